@@ -1,0 +1,362 @@
+// C ABI of libdiffpose_b200.so: handle lifetime, weight packing, engine dispatch.
+// See include/diffpose_b200.h for the contract and the reference interfaces each entry point replaces.
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <new>
+#include "dp_internal.h"
+
+namespace dp {
+
+static thread_local std::string g_err;
+static std::atomic<long> g_launches{0};
+
+void set_error(const std::string& msg) { g_err = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int ensure_capacity(float** p, size_t* cap, size_t need_floats) {
+  if (*cap >= need_floats && *p != nullptr) return DP_OK;
+  if (*p) cudaFree(*p);
+  *p = nullptr;
+  *cap = 0;
+  size_t n = need_floats < 1024 ? 1024 : need_floats;
+  DP_CUDA(cudaMalloc(reinterpret_cast<void**>(p), n * sizeof(float)));
+  *cap = n;
+  return DP_OK;
+}
+
+// dst[k*ld + col0 + n] = src[n*K + k]: a torch.nn.Linear weight [N][K] becomes an input-major [K][N] panel.
+__global__ void pack_transpose_kernel(float* __restrict__ dst, const float* __restrict__ src, int K, int N, int ld,
+                                      int col0) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= K * N) return;
+  int k = idx / N, n = idx - k * N;
+  dst[(size_t)k * ld + col0 + n] = src[(size_t)n * K + k];
+}
+
+__global__ void pack_copy_kernel(float* __restrict__ dst, const float* __restrict__ src, int rows, int cols, int ld,
+                                 int col0) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  int r = idx / cols, c = idx - r * cols;
+  dst[(size_t)r * ld + col0 + c] = src[idx];
+}
+
+// GraFormer.py:174-178: D_j = (sum_i A[i][j] + 1e-5)^-1/2 ; Lhat[i][j] = D_i * A[i][j] * D_j.
+__global__ void pack_lhat_kernel(float* __restrict__ dst, const float* __restrict__ a_hat, int n) {
+  __shared__ float d[32];
+  int j = threadIdx.x;
+  if (j < n) {
+    float s = 0.f;
+    for (int i = 0; i < n; ++i) s += a_hat[i * n + j];
+    d[j] = 1.0f / sqrtf(s + 1e-5f);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
+    int i = idx / n, jj = idx - i * n;
+    dst[idx] = d[i] * a_hat[idx] * d[jj];
+  }
+}
+
+struct Carver {
+  float* base;
+  size_t off = 0;
+  explicit Carver(float* b) : base(b) {}
+  float* take(size_t n) {
+    float* p = base ? base + off : nullptr;
+    off += (n + 31) & ~size_t(31);  // 128-byte aligned panels
+    return p;
+  }
+};
+
+// Lays the packed fp32 blob out; with base == nullptr only measures it.
+static size_t carve(Weights& w, const Dims& d, float* base) {
+  Carver c(base);
+  const int H = d.hid, P = d.n_pts * d.n_pts;
+  w.win = c.take((size_t)3 * d.c_in * H);
+  w.bin = c.take(H);
+  w.wout = c.take((size_t)3 * H * d.c_out);
+  w.bout = c.take(d.c_out);
+  w.t1 = c.take(P);
+  w.t2 = c.take(P);
+  w.wd0 = c.take((size_t)H * 4 * H);
+  w.bd0 = c.take(4 * H);
+  w.wd1 = c.take((size_t)16 * H * H);
+  w.bd1 = c.take(4 * H);
+  for (int l = 0; l < d.n_layer; ++l) {
+    LayerW& L = w.layer[l];
+    L.ln0_a = c.take(H); L.ln0_b = c.take(H);
+    L.wqkv = c.take((size_t)3 * H * H); L.bqkv = c.take(3 * H);
+    L.wo = c.take((size_t)H * H); L.bo = c.take(H);
+    L.ln1_a = c.take(H); L.ln1_b = c.take(H);
+    L.lhat = c.take(P);
+    L.w1 = c.take((size_t)2 * H * H); L.b1 = c.take(2 * H);
+    L.w2 = c.take((size_t)2 * H * H); L.b2 = c.take(H);
+    L.wc1 = c.take((size_t)3 * H * H); L.bc1 = c.take(H);
+    L.wc2 = c.take((size_t)3 * H * H); L.bc2 = c.take(H);
+    L.wt = c.take((size_t)4 * H * H); L.bt = c.take(H);
+  }
+  return c.off;
+}
+
+static long param_count(const Dims& d) {
+  const long H = d.hid, P = (long)d.n_pts * d.n_pts;
+  long n = 3L * d.c_in * H + H;
+  long per = 2 * (3 * H * H + H) + 4 * (H * H + H) + P + (2 * H * H + 2 * H) + (2 * H * H + H) + 4 * H;
+  if (d.has_temb) per += 4 * H * H + H;
+  n += per * d.n_layer;
+  n += 3L * H * d.c_out + d.c_out;
+  if (d.has_temb) n += (4 * H * H + 4 * H) + (16 * H * H + 4 * H);
+  return n;
+}
+
+static inline float* mut(const float* p) { return const_cast<float*>(p); }
+
+static int launch_transpose(float* dst, const float* src, int K, int N, int ld, int col0, cudaStream_t s) {
+  int total = K * N;
+  pack_transpose_kernel<<<(total + 255) / 256, 256, 0, s>>>(dst, src, K, N, ld, col0);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
+static int launch_copy(float* dst, const float* src, int rows, int cols, int ld, int col0, cudaStream_t s) {
+  int total = rows * cols;
+  pack_copy_kernel<<<(total + 255) / 256, 256, 0, s>>>(dst, src, rows, cols, ld, col0);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
+
+static int pack_fp32(dp_model* m, const float* p, const float* adj_host, cudaStream_t s) {
+  const Dims& d = m->d;
+  const int H = d.hid, NP = d.n_pts, P = NP * NP;
+  const Weights& w = m->hw;
+
+  DP_TRY(launch_copy(mut(w.win), p, 3 * d.c_in, H, H, 0, s)); p += 3 * d.c_in * H;
+  DP_TRY(launch_copy(mut(w.bin), p, 1, H, H, 0, s)); p += H;
+  for (int l = 0; l < d.n_layer; ++l) {
+    const LayerW& L = w.layer[l];
+    DP_TRY(launch_copy(mut(L.wc1), p, 3 * H, H, H, 0, s)); p += 3 * H * H;
+    DP_TRY(launch_copy(mut(L.bc1), p, 1, H, H, 0, s)); p += H;
+    DP_TRY(launch_copy(mut(L.wc2), p, 3 * H, H, H, 0, s)); p += 3 * H * H;
+    DP_TRY(launch_copy(mut(L.bc2), p, 1, H, H, 0, s)); p += H;
+    if (d.has_temb) {
+      DP_TRY(launch_transpose(mut(L.wt), p, 4 * H, H, H, 0, s)); p += 4 * H * H;
+      DP_TRY(launch_copy(mut(L.bt), p, 1, H, H, 0, s)); p += H;
+    }
+    for (int i = 0; i < 3; ++i) {
+      DP_TRY(launch_transpose(mut(L.wqkv), p, H, H, 3 * H, i * H, s)); p += H * H;
+      DP_TRY(launch_copy(mut(L.bqkv), p, 1, H, 3 * H, i * H, s)); p += H;
+    }
+    DP_TRY(launch_transpose(mut(L.wo), p, H, H, H, 0, s)); p += H * H;
+    DP_TRY(launch_copy(mut(L.bo), p, 1, H, H, 0, s)); p += H;
+    pack_lhat_kernel<<<1, 32, 0, s>>>(mut(L.lhat), p, NP);
+    count_launch();
+    DP_CUDA(cudaGetLastError());
+    p += P;
+    DP_TRY(launch_transpose(mut(L.w1), p, H, 2 * H, 2 * H, 0, s)); p += 2 * H * H;
+    DP_TRY(launch_copy(mut(L.b1), p, 1, 2 * H, 2 * H, 0, s)); p += 2 * H;
+    DP_TRY(launch_transpose(mut(L.w2), p, 2 * H, H, H, 0, s)); p += 2 * H * H;
+    DP_TRY(launch_copy(mut(L.b2), p, 1, H, H, 0, s)); p += H;
+    DP_TRY(launch_copy(mut(L.ln0_a), p, 1, H, H, 0, s)); p += H;
+    DP_TRY(launch_copy(mut(L.ln0_b), p, 1, H, H, 0, s)); p += H;
+    DP_TRY(launch_copy(mut(L.ln1_a), p, 1, H, H, 0, s)); p += H;
+    DP_TRY(launch_copy(mut(L.ln1_b), p, 1, H, H, 0, s)); p += H;
+  }
+  DP_TRY(launch_copy(mut(w.wout), p, 3 * H, d.c_out, d.c_out, 0, s)); p += 3 * H * d.c_out;
+  DP_TRY(launch_copy(mut(w.bout), p, 1, d.c_out, d.c_out, 0, s)); p += d.c_out;
+  if (d.has_temb) {
+    DP_TRY(launch_transpose(mut(w.wd0), p, H, 4 * H, 4 * H, 0, s)); p += 4 * H * H;
+    DP_TRY(launch_copy(mut(w.bd0), p, 1, 4 * H, 4 * H, 0, s)); p += 4 * H;
+    DP_TRY(launch_transpose(mut(w.wd1), p, 4 * H, 4 * H, 4 * H, 0, s)); p += 16 * H * H;
+    DP_TRY(launch_copy(mut(w.bd1), p, 1, 4 * H, 4 * H, 0, s)); p += 4 * H;
+  }
+
+  // Chebyshev basis on the host, fp32 like the reference (models/ChebConv.py:90-130):
+  // D = diag(rowsum^-1/2), L = I - D A D, T1 = L, T2 = 2 L L - I.
+  std::vector<float> dg(NP), lap(P), t2(P);
+  for (int i = 0; i < NP; ++i) {
+    float rs = 0.f;
+    for (int j = 0; j < NP; ++j) rs += adj_host[i * NP + j];
+    dg[i] = 1.0f / std::sqrt(rs);
+  }
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) lap[i * NP + j] = (i == j ? 1.f : 0.f) - (dg[i] * adj_host[i * NP + j]) * dg[j];
+  for (int i = 0; i < NP; ++i)
+    for (int j = 0; j < NP; ++j) {
+      float acc = 0.f;
+      for (int k = 0; k < NP; ++k) acc += lap[i * NP + k] * lap[k * NP + j];
+      t2[i * NP + j] = 2.f * acc - (i == j ? 1.f : 0.f);
+    }
+  DP_CUDA(cudaMemcpyAsync(mut(w.t1), lap.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
+  DP_CUDA(cudaMemcpyAsync(mut(w.t2), t2.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
+  DP_CUDA(cudaMemcpyAsync(m->dw, &m->hw, sizeof(Weights), cudaMemcpyHostToDevice, s));
+  // the host vectors above go out of scope: finish the copies first (pack is not on the hot path)
+  DP_CUDA(cudaStreamSynchronize(s));
+  return DP_OK;
+}
+
+}  // namespace dp
+
+using namespace dp;
+
+extern "C" {
+
+int dp_create(dp_handle* out, int n_pts, int c_in, int c_out, int hid, int n_layer, int n_head, int has_temb) {
+  DP_REQUIRE(out != nullptr, "dp_create: out is NULL");
+  *out = nullptr;
+  DP_REQUIRE(n_pts == kMaxPts, "dp_create: kernels are built for the 17-joint Human3.6M skeleton (n_pts must be 17)");
+  DP_REQUIRE(c_in >= 1 && c_in <= kMaxCoord && c_out >= 1 && c_out <= kMaxCoord, "dp_create: coords_dim must be in 1..8");
+  DP_REQUIRE(hid >= 32 && hid <= 128 && hid % 32 == 0, "dp_create: hid_dim must be 32, 64, 96 or 128");
+  DP_REQUIRE(n_layer >= 1 && n_layer <= kMaxLayers, "dp_create: num_layer must be in 1..16");
+  DP_REQUIRE(n_head >= 1 && hid % n_head == 0 && hid / n_head <= 64, "dp_create: n_head must divide hid_dim with d_k <= 64");
+  DP_REQUIRE(!has_temb || c_in == c_out, "dp_create: the diffusion denoiser needs coords_dim[0] == coords_dim[1]");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("dp_create: no CUDA device is visible; this library has no CPU path");
+    return DP_ERR_CUDA;
+  }
+  dp_model* m = new (std::nothrow) dp_model();
+  DP_REQUIRE(m != nullptr, "dp_create: out of host memory");
+  m->d = Dims{n_pts, c_in, c_out, hid, n_layer, n_head, has_temb ? 1 : 0};
+  m->n_params = param_count(m->d);
+  cudaError_t e = cudaGetDevice(&m->device);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&m->sm_count, cudaDevAttrMultiProcessorCount, m->device);
+  if (e == cudaSuccess) {
+    Weights tmp{};
+    m->blob_floats = carve(tmp, m->d, nullptr);
+    e = cudaMalloc(reinterpret_cast<void**>(&m->blob), m->blob_floats * sizeof(float));
+  }
+  if (e == cudaSuccess) e = cudaMemset(m->blob, 0, m->blob_floats * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(reinterpret_cast<void**>(&m->dw), sizeof(Weights));
+  if (e != cudaSuccess) {
+    set_error(std::string("dp_create: ") + cudaGetErrorString(e));
+    dp_destroy(m);
+    return DP_ERR_CUDA;
+  }
+  carve(m->hw, m->d, m->blob);
+  *out = m;
+  return DP_OK;
+}
+
+long dp_param_count(dp_handle h) { return h ? h->n_params : -1; }
+
+int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_host, void* stream) {
+  DP_REQUIRE(h && params && adj_host, "dp_pack: NULL argument");
+  if (n_floats != h->n_params) {
+    set_error("dp_pack: expected " + std::to_string(h->n_params) + " floats, got " + std::to_string(n_floats));
+    return DP_ERR_INVALID;
+  }
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DP_TRY(pack_fp32(h, params, adj_host, s));
+  if (tc_supported(h->d)) DP_TRY(tc_pack(h, s));
+  h->packed = true;
+  return DP_OK;
+}
+
+int dp_set_engine(dp_handle h, int engine) {
+  DP_REQUIRE(h, "dp_set_engine: NULL handle");
+  DP_REQUIRE(engine == DP_ENGINE_AUTO || engine == DP_ENGINE_FP32 || engine == DP_ENGINE_TC, "dp_set_engine: unknown engine");
+  if (engine == DP_ENGINE_TC && !tc_supported(h->d)) {
+    set_error("dp_set_engine: the tensor-core engine needs hid_dim=96, n_head=4, n_pts=17");
+    return DP_ERR_UNSUPPORTED;
+  }
+  h->engine = engine;
+  return DP_OK;
+}
+
+int dp_get_engine(dp_handle h) {
+  if (!h) return DP_ERR_INVALID;
+  if (h->engine == DP_ENGINE_FP32) return DP_ENGINE_FP32;
+  return tc_supported(h->d) ? DP_ENGINE_TC : DP_ENGINE_FP32;
+}
+
+int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char* mask, float* out, long n, void* stream) {
+  DP_REQUIRE(h && x && out, "dp_forward: NULL argument");
+  DP_REQUIRE(n >= 0, "dp_forward: negative batch");
+  if (!h->packed) { set_error("dp_forward: dp_pack has not been called"); return DP_ERR_STATE; }
+  DP_REQUIRE(!h->d.has_temb || t != nullptr, "dp_forward: t is required for the diffusion denoiser");
+  if (n == 0) return DP_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // Per-sample timesteps need a per-sample embedding table; the fp32 engine serves this entry point.
+  return simt_forward(h, x, t, mask, out, n, s);
+}
+
+int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+              const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
+              int mean_over_hyp, void* stream) {
+  DP_REQUIRE(h && x_in && x_out && steps_host, "dp_sample: NULL argument");
+  DP_REQUIRE(n_pose >= 0 && n_hyp >= 1 && n_steps >= 1, "dp_sample: n_pose >= 0, n_hyp >= 1, n_steps >= 1 required");
+  DP_REQUIRE(h->d.has_temb, "dp_sample: handle was created with has_temb = 0 (GCNpose has no sampler)");
+  if (!h->packed) { set_error("dp_sample: dp_pack has not been called"); return DP_ERR_STATE; }
+  if (n_pose == 0) return DP_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const Dims& d = h->d;
+
+  StepsArg inl{};
+  const dp_step* steps_dev = nullptr;
+  if (n_steps <= kMaxInlineSteps) {
+    std::memcpy(inl.s, steps_host, n_steps * sizeof(dp_step));
+  } else {
+    if (h->steps_cap < (size_t)n_steps) {
+      if (h->steps) cudaFree(h->steps);
+      h->steps = nullptr; h->steps_cap = 0;
+      DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->steps), (size_t)n_steps * sizeof(dp_step)));
+      h->steps_cap = n_steps;
+    }
+    // long schedules only: steps_host is caller (possibly pageable) memory, so finish the copy before returning
+    DP_CUDA(cudaMemcpyAsync(h->steps, steps_host, n_steps * sizeof(dp_step), cudaMemcpyHostToDevice, s));
+    DP_CUDA(cudaStreamSynchronize(s));
+    steps_dev = h->steps;
+  }
+  // batch-invariant time embeddings: one row per step (models/gcndiff.py:103-106, :51)
+  DP_TRY(simt_temb(h, steps_dev ? &steps_dev->t : nullptr, sizeof(dp_step) / sizeof(float), &inl, n_steps, s));
+
+  float* dst = x_out;
+  const int row_floats = d.n_pts * d.c_out;
+  if (mean_over_hyp && n_hyp > 1) {
+    DP_TRY(ensure_capacity(&h->hyp_scratch, &h->hyp_cap, (size_t)n_pose * n_hyp * row_floats));
+    dst = h->hyp_scratch;
+  }
+  int rc;
+  if (dp_get_engine(h) == DP_ENGINE_TC)
+    rc = tc_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
+  else
+    rc = simt_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
+  if (rc != DP_OK) return rc;
+  if (mean_over_hyp && n_hyp > 1) DP_TRY(hyp_mean_launch(dst, x_out, n_pose, n_hyp, row_floats, s));
+  return DP_OK;
+}
+
+int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
+               double* sums, float* per_pose, void* stream) {
+  DP_REQUIRE(pred && gt && sums, "dp_metrics: NULL argument");
+  DP_REQUIRE(n_pts == kMaxPts, "dp_metrics: n_pts must be 17");
+  DP_REQUIRE(pred_stride >= 3 && pred_offset >= 0 && pred_offset + 3 <= pred_stride, "dp_metrics: bad pred stride/offset");
+  if (n <= 0) return n == 0 ? DP_OK : DP_ERR_INVALID;
+  return metrics_launch(pred, pred_stride, pred_offset, gt, n, n_pts, sums, per_pose, static_cast<cudaStream_t>(stream));
+}
+
+long dp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int dp_last_launch_info(dp_handle h, long* out6) {
+  DP_REQUIRE(h && out6, "dp_last_launch_info: NULL argument");
+  for (int i = 0; i < 6; ++i) out6[i] = h->last_launch[i];
+  return DP_OK;
+}
+
+const char* dp_last_error(void) { return g_err.c_str(); }
+const char* dp_version(void) { return "diffpose_b200 0.1 (sm_100a)"; }
+
+void dp_destroy(dp_handle h) {
+  if (!h) return;
+  tc_free(h);
+  if (h->blob) cudaFree(h->blob);
+  if (h->dw) cudaFree(h->dw);
+  if (h->temb) cudaFree(h->temb);
+  if (h->steps) cudaFree(h->steps);
+  if (h->hyp_scratch) cudaFree(h->hyp_scratch);
+  delete h;
+}
+
+}  // extern "C"

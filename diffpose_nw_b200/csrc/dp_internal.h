@@ -1,0 +1,126 @@
+// Internal declarations shared by the translation units of libdiffpose_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/diffpose_b200.h"
+
+namespace dp {
+
+constexpr int kMaxLayers = 16;
+constexpr int kMaxPts = 17;       // the kernels are written for the 17-joint Human3.6M skeleton
+constexpr int kMaxCoord = 8;      // c_in / c_out upper bound (uvxyz = 5)
+
+struct Dims {
+  int n_pts, c_in, c_out, hid, n_layer, n_head, has_temb;
+};
+
+// fp32 weights of one GraAttenLayer + _ResChebGC(_diff) pair, every matrix stored [K][N] row-major
+// (K = input feature, N = output feature) so that a warp reads consecutive output features.
+struct LayerW {
+  const float *ln0_a, *ln0_b;   // atten_layers.l.sublayer.0.norm
+  const float *wqkv, *bqkv;     // [hid][3hid] = linears.0|1|2 side by side
+  const float *wo, *bo;         // [hid][hid]   linears.3
+  const float *ln1_a, *ln1_b;   // sublayer.1.norm
+  const float *lhat;            // [n_pts][n_pts]  D A_hat D  (GraFormer.py:174-178)
+  const float *w1, *b1;         // [hid][2hid]  feed_forward.gconv1.fc
+  const float *w2, *b2;         // [2hid][hid]  feed_forward.gconv2.fc
+  const float *wc1, *bc1;       // [3hid][hid]  gconv_layers.l.gconv1.gconv  (k = cheb_order*hid + c)
+  const float *wc2, *bc2;       // [3hid][hid]  gconv_layers.l.gconv2.gconv
+  const float *wt, *bt;         // [4hid][hid]  gconv_layers.l.temb_proj (has_temb)
+};
+
+struct Weights {
+  const float *win, *bin;       // [3c_in][hid]
+  const float *wout, *bout;     // [3hid][c_out]
+  const float *t1, *t2;         // Chebyshev T1 = L, T2 = 2L^2 - I, [n_pts][n_pts]
+  const float *wd0, *bd0;       // [hid][4hid]  temb.dense.0
+  const float *wd1, *bd1;       // [4hid][4hid] temb.dense.1
+  LayerW layer[kMaxLayers];
+};
+
+void set_error(const std::string& msg);
+void count_launch(int n = 1);
+
+#define DP_CUDA(expr)                                                                              \
+  do {                                                                                             \
+    cudaError_t _e = (expr);                                                                       \
+    if (_e != cudaSuccess) {                                                                       \
+      dp::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e));                           \
+      return DP_ERR_CUDA;                                                                          \
+    }                                                                                              \
+  } while (0)
+
+#define DP_REQUIRE(cond, msg)                                                                      \
+  do {                                                                                             \
+    if (!(cond)) {                                                                                 \
+      dp::set_error(std::string(msg));                                                             \
+      return DP_ERR_INVALID;                                                                       \
+    }                                                                                              \
+  } while (0)
+
+#define DP_TRY(expr)              \
+  do {                            \
+    int _rc = (expr);             \
+    if (_rc != DP_OK) return _rc; \
+  } while (0)
+
+// DDIM step scalars travel as a by-value kernel argument (no host->device copy, graph friendly).
+constexpr int kMaxInlineSteps = 64;
+struct StepsArg {
+  dp_step s[kMaxInlineSteps];
+};
+
+struct TcPack;  // defined in dp_tc.cu
+
+}  // namespace dp
+
+// The opaque handle.
+struct dp_model {
+  dp::Dims d{};
+  int device = 0;
+  int sm_count = 0;
+  int engine = DP_ENGINE_AUTO;
+  bool packed = false;
+  long n_params = 0;
+
+  float* blob = nullptr;          // packed fp32 weights
+  size_t blob_floats = 0;
+  dp::Weights hw{};               // host copy of the device pointers
+  dp::Weights* dw = nullptr;      // the same struct in device memory
+
+  float* temb = nullptr;          // [n_rows][n_layer][hid] time-embedding table scratch
+  size_t temb_cap = 0;            // capacity in floats
+  dp_step* steps = nullptr;       // device copy of the step scalars, only used when n_steps > kMaxInlineSteps
+  size_t steps_cap = 0;
+  float* hyp_scratch = nullptr;   // [n_pose*n_hyp, n_pts, c] when the hypothesis mean is fused after sampling
+  size_t hyp_cap = 0;
+
+  dp::TcPack* tc = nullptr;       // tensor-core engine state (fp16 packed weights, ...)
+  long last_launch[6] = {0, 0, 0, 0, 0, 0};
+};
+
+namespace dp {
+// dp_simt.cu
+// time-embedding table [n_t][n_layer][hid]: t comes from t_dev[i*t_stride] or, when t_dev is NULL, from inl.s[i].t
+int simt_temb(dp_model* m, const float* t_dev, int t_stride, const StepsArg* inl, long n_t, cudaStream_t s);
+int simt_forward(dp_model* m, const float* x, const float* t, const unsigned char* mask, float* out, long n,
+                 cudaStream_t s);
+int simt_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+                const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
+                const unsigned char* mask, cudaStream_t s);
+int ensure_capacity(float** p, size_t* cap, size_t need_floats);
+// dp_tc.cu
+bool tc_supported(const Dims& d);
+int tc_pack(dp_model* m, cudaStream_t s);
+void tc_free(dp_model* m);
+int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+              const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
+              const unsigned char* mask, cudaStream_t s);
+// dp_metrics.cu
+int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
+                   double* sums, float* per_pose, cudaStream_t s);
+int hyp_mean_launch(const float* x, float* out, long n_pose, int n_hyp, int row_floats, cudaStream_t s);
+}  // namespace dp

@@ -1,0 +1,221 @@
+// Evaluation kernels that follow the sampler: hypothesis mean, MPJPE and Procrustes-aligned MPJPE.
+//   hypothesis mean   runners/diffpose_frame.py:382
+//   mpjpe             common/loss.py:7-13 (after root-centring, runners/diffpose_frame.py:384-386)
+//   p_mpjpe           common/loss.py:25-64 == common/utils.py:155-187 (numpy float64 SVD in the reference;
+//                     here a one-sided Jacobi SVD of the 3x3 cross-covariance in fp64, one thread per pose)
+#include "dp_internal.h"
+
+namespace dp {
+namespace {
+
+constexpr int NP = 17;
+
+__global__ void hyp_mean_kernel(const float* __restrict__ x, float* __restrict__ out, long n_pose, int n_hyp,
+                                int row_floats) {
+  const long total = n_pose * row_floats;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int h = 0; h < n_hyp; ++h) s += x[(size_t)h * total + i];
+    out[i] = s / (float)n_hyp;
+  }
+}
+
+__device__ inline void rot_cols(double a[3][3], int p, int q, double c, double s) {
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const double ap = a[r][p], aq = a[r][q];
+    a[r][p] = c * ap - s * aq;
+    a[r][q] = s * ap + c * aq;
+  }
+}
+
+// H = U diag(sv) V^T with sv sorted descending; U, V orthogonal (U completed by a cross product when rank < 3).
+__device__ void svd3(const double h[3][3], double u[3][3], double sv[3], double v[3][3]) {
+  double a[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { a[i][j] = h[i][j]; v[i][j] = (i == j) ? 1.0 : 0.0; }
+  for (int sweep = 0; sweep < 30; ++sweep) {
+    double off = 0.0;
+#pragma unroll
+    for (int pair = 0; pair < 3; ++pair) {
+      const int p = pair == 2 ? 1 : 0, q = pair == 0 ? 1 : 2;
+      double alpha = 0, beta = 0, gamma = 0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { alpha += a[r][p] * a[r][p]; beta += a[r][q] * a[r][q]; gamma += a[r][p] * a[r][q]; }
+      const double lim = 1e-15 * sqrt(alpha * beta);
+      if (fabs(gamma) > lim && fabs(gamma) > 1e-300) {
+        off += fabs(gamma);
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
+        rot_cols(a, p, q, c, s);
+        rot_cols(v, p, q, c, s);
+      }
+    }
+    if (off == 0.0) break;
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) sv[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
+  // sort columns by descending singular value (3-element network)
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    const int p = pass == 1 ? 1 : 0, q = p + 1;
+    if (sv[p] < sv[q]) {
+      double t = sv[p]; sv[p] = sv[q]; sv[q] = t;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        t = a[r][p]; a[r][p] = a[r][q]; a[r][q] = t;
+        t = v[r][p]; v[r][p] = v[r][q]; v[r][q] = t;
+      }
+    }
+  }
+  const double tiny = 1e-14 * (sv[0] > 0 ? sv[0] : 1.0);
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    if (sv[j] > tiny) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) u[r][j] = a[r][j] / sv[j];
+    }
+  }
+  if (sv[1] <= tiny) {  // rank <= 1: any unit vector orthogonal to u0
+    double ax = fabs(u[0][0]), ay = fabs(u[1][0]), az = fabs(u[2][0]);
+    double e[3] = {0, 0, 0};
+    e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
+    double w0 = u[1][0] * e[2] - u[2][0] * e[1], w1 = u[2][0] * e[0] - u[0][0] * e[2], w2 = u[0][0] * e[1] - u[1][0] * e[0];
+    const double n = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    u[0][1] = w0 / n; u[1][1] = w1 / n; u[2][1] = w2 / n;
+  }
+  if (sv[2] <= tiny) {
+    u[0][2] = u[1][0] * u[2][1] - u[2][0] * u[1][1];
+    u[1][2] = u[2][0] * u[0][1] - u[0][0] * u[2][1];
+    u[2][2] = u[0][0] * u[1][1] - u[1][0] * u[0][1];
+  }
+}
+
+__device__ inline double det3(const double m[3][3]) {
+  return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
+         m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+}
+
+__global__ void metrics_kernel(const float* __restrict__ pred, int ps, int po, const float* __restrict__ gt, long n,
+                               double* __restrict__ sums, float* __restrict__ per_pose) {
+  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+  double e1 = 0.0, e2 = 0.0, cnt = 0.0;
+  if (i < n) {
+    double X[NP][3], Y[NP][3];  // X = target, Y = predicted, both root-centred (out of place)
+    const float* p = pred + (size_t)i * NP * ps + po;
+    const float* g = gt + (size_t)i * NP * 3;
+    const float pr[3] = {p[0], p[1], p[2]}, gr[3] = {g[0], g[1], g[2]};
+    float acc = 0.f;
+    for (int j = 0; j < NP; ++j) {
+      float d2 = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const float pv = p[j * ps + c] - pr[c], gv = g[j * 3 + c] - gr[c];
+        Y[j][c] = pv; X[j][c] = gv;
+        const float df = pv - gv;
+        d2 += df * df;
+      }
+      acc += sqrtf(d2);
+    }
+    e1 = (double)(acc / (float)NP);
+
+    double mx[3] = {0, 0, 0}, my[3] = {0, 0, 0};
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) { mx[c] += X[j][c]; my[c] += Y[j][c]; }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { mx[c] /= NP; my[c] /= NP; }
+    double nx = 0, ny = 0;
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double a = X[j][c] - mx[c], b = Y[j][c] - my[c];
+        nx += a * a; ny += b * b;
+      }
+    nx = sqrt(nx); ny = sqrt(ny);
+    double h[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // H = X0^T Y0
+    for (int j = 0; j < NP; ++j)
+#pragma unroll
+      for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int b = 0; b < 3; ++b) h[a][b] += ((X[j][a] - mx[a]) / nx) * ((Y[j][b] - my[b]) / ny);
+    double u[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, v[3][3], sv[3];
+    svd3(h, u, sv, v);
+    double r[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) r[a][b] = v[a][0] * u[b][0] + v[a][1] * u[b][1] + v[a][2] * u[b][2];
+    const double dt = det3(r);
+    const double sg = dt > 0 ? 1.0 : (dt < 0 ? -1.0 : 0.0);
+#pragma unroll
+    for (int a = 0; a < 3; ++a) v[a][2] *= sg;
+    sv[2] *= sg;
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) r[a][b] = v[a][0] * u[b][0] + v[a][1] * u[b][1] + v[a][2] * u[b][2];
+    const double scale = (sv[0] + sv[1] + sv[2]) * nx / ny;
+    double tr[3];
+#pragma unroll
+    for (int b = 0; b < 3; ++b) tr[b] = mx[b] - scale * (my[0] * r[0][b] + my[1] * r[1][b] + my[2] * r[2][b]);
+    double err = 0.0;
+    for (int j = 0; j < NP; ++j) {
+      double d2 = 0.0;
+#pragma unroll
+      for (int b = 0; b < 3; ++b) {
+        const double al = scale * (Y[j][0] * r[0][b] + Y[j][1] * r[1][b] + Y[j][2] * r[2][b]) + tr[b];
+        const double df = al - X[j][b];
+        d2 += df * df;
+      }
+      err += sqrt(d2);
+    }
+    e2 = err / NP;
+    cnt = 1.0;
+    if (per_pose) { per_pose[2 * i] = (float)e1; per_pose[2 * i + 1] = (float)e2; }
+  }
+  // block reduction -> one atomic per block and quantity
+  __shared__ double red[3][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    e1 += __shfl_xor_sync(0xffffffffu, e1, o);
+    e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+  }
+  if (lane == 0) { red[0][warp] = e1; red[1][warp] = e2; red[2][warp] = cnt; }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double s = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
+    atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+}  // namespace
+
+int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
+                   double* sums, float* per_pose, cudaStream_t s) {
+  (void)n_pts;
+  const int block = 128;
+  const long grid = (n + block - 1) / block;
+  metrics_kernel<<<(unsigned)grid, block, 0, s>>>(pred, pred_stride, pred_offset, gt, n, sums, per_pose);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
+
+int hyp_mean_launch(const float* x, float* out, long n_pose, int n_hyp, int row_floats, cudaStream_t s) {
+  const long total = n_pose * row_floats;
+  long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  hyp_mean_kernel<<<(unsigned)grid, 256, 0, s>>>(x, out, n_pose, n_hyp, row_floats);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
+
+}  // namespace dp

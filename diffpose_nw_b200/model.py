@@ -1,0 +1,277 @@
+"""Drop-in modules for the reference's frame-based denoiser and stage-1 lifter.
+
+`FusedGCNdiff(adj, config)` replaces `GCNdiff(adj, config)` (reference models/gcndiff.py:55-113) and
+`FusedGCNpose(adj, config)` replaces `GCNpose(adj, config)` (reference models/gcnpose.py:55-113):
+
+* same constructor arguments and config keys (`config.model.{hid_dim, emd_dim, coords_dim, num_layer, n_head,
+  dropout, n_pts}`), `emd_dim` overridden by `4*hid_dim` exactly as the reference does (gcndiff.py:68);
+* same `state_dict` keys and shapes, so `load_state_dict(states[0])` of a reference
+  checkpoint works unchanged, with or without DataParallel's `module.` prefix;
+* same default initialisation *and the same RNG draw order* as the reference constructor, so
+  `torch.manual_seed(s); FusedGCNdiff(adj, cfg)` holds bit-identical weights to `torch.manual_seed(s);
+  GCNdiff(adj, cfg)` (the reference deep-copies one attention block and one GraphNet into every layer,
+  gcndiff.py:78-85; that is reproduced);
+* same forward signatures `model(x, mask, t, cemd)` / `model(x, mask)`.
+
+The modules only hold parameters; all arithmetic happens in libdiffpose_b200.so on the GPU.  There is no CPU or
+eager-PyTorch fallback: calling forward with CPU tensors raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+
+class _ChebParams(nn.Module):
+    """Parameters of one ChebConv(in_c, out_c, K=2) (reference models/ChebConv.py:59-70)."""
+
+    def __init__(self, in_c, out_c):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(3, 1, in_c, out_c))
+        nn.init.xavier_normal_(self.weight)
+        self.bias = nn.Parameter(torch.zeros(1, 1, out_c))
+
+
+class _GraphConvParams(nn.Module):
+    def __init__(self, in_c, out_c):
+        super().__init__()
+        self.gconv = _ChebParams(in_c, out_c)
+
+
+class _ResChebParams(nn.Module):
+    """gconv_layers.l: two graph convolutions (+ temb_proj for the diffusion denoiser)."""
+
+    def __init__(self, hid, emd, with_temb):
+        super().__init__()
+        self.gconv1 = _GraphConvParams(hid, hid)
+        self.gconv2 = _GraphConvParams(hid, hid)
+        if with_temb:
+            self.temb_proj = nn.Linear(emd, hid)
+
+
+class _AttnParams(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        first = nn.Linear(hid, hid)  # the reference clones ONE Linear four times (GraFormer.py:123)
+        self.linears = nn.ModuleList([first] + [_clone(first) for _ in range(3)])
+
+
+class _LamParams(nn.Module):
+    def __init__(self, in_f, out_f):
+        super().__init__()
+        self.fc = nn.Linear(in_f, out_f)
+
+
+class _GraphNetParams(nn.Module):
+    def __init__(self, hid, n_pts):
+        super().__init__()
+        self.A_hat = nn.Parameter(torch.eye(n_pts))
+        self.gconv1 = _LamParams(hid, 2 * hid)
+        self.gconv2 = _LamParams(2 * hid, hid)
+
+
+class _NormParams(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        self.a_2 = nn.Parameter(torch.ones(hid))
+        self.b_2 = nn.Parameter(torch.zeros(hid))
+
+
+class _SublayerParams(nn.Module):
+    def __init__(self, hid):
+        super().__init__()
+        self.norm = _NormParams(hid)
+
+
+class _AttenLayerParams(nn.Module):
+    def __init__(self, hid, attn, ffn):
+        super().__init__()
+        self.self_attn = attn
+        self.feed_forward = ffn
+        self.sublayer = nn.ModuleList([_SublayerParams(hid), _SublayerParams(hid)])
+
+
+def _clone(module):
+    import copy
+    return copy.deepcopy(module)
+
+
+def _param_order(n_layer, has_temb):
+    """Canonical flattening order documented in include/diffpose_b200.h (dp_pack)."""
+    keys = ["gconv_input.weight", "gconv_input.bias"]
+    for l in range(n_layer):
+        g, a = f"gconv_layers.{l}", f"atten_layers.{l}"
+        keys += [f"{g}.gconv1.gconv.weight", f"{g}.gconv1.gconv.bias", f"{g}.gconv2.gconv.weight", f"{g}.gconv2.gconv.bias"]
+        if has_temb:
+            keys += [f"{g}.temb_proj.weight", f"{g}.temb_proj.bias"]
+        for i in range(4):
+            keys += [f"{a}.self_attn.linears.{i}.weight", f"{a}.self_attn.linears.{i}.bias"]
+        keys += [f"{a}.feed_forward.A_hat", f"{a}.feed_forward.gconv1.fc.weight", f"{a}.feed_forward.gconv1.fc.bias",
+                 f"{a}.feed_forward.gconv2.fc.weight", f"{a}.feed_forward.gconv2.fc.bias",
+                 f"{a}.sublayer.0.norm.a_2", f"{a}.sublayer.0.norm.b_2", f"{a}.sublayer.1.norm.a_2", f"{a}.sublayer.1.norm.b_2"]
+    keys += ["gconv_output.weight", "gconv_output.bias"]
+    if has_temb:
+        keys += ["temb.dense.0.weight", "temb.dense.0.bias", "temb.dense.1.weight", "temb.dense.1.bias"]
+    return keys
+
+
+class _FusedBase(nn.Module):
+    _has_temb = True
+
+    def __init__(self, adj, config):
+        super().__init__()
+        self.adj = adj                      # plain attribute, not a buffer (reference gcndiff.py:59)
+        self.config = config
+        m = config.model
+        self.hid_dim, self.coords_dim = m.hid_dim, list(m.coords_dim)
+        self.emd_dim = self.hid_dim * 4     # YAML emd_dim is ignored by the reference (gcndiff.py:68)
+        self.n_layers, self.n_head, self.n_pts = m.num_layer, m.n_head, m.n_pts
+        hid, c_in, c_out = self.hid_dim, self.coords_dim[0], self._out_dim()
+
+        # --- parameters, created in the reference's order so the RNG stream matches (gcndiff.py:73-98)
+        gconv_input = _ChebParams(c_in, hid)
+        attn = _AttnParams(hid)
+        ffn = _GraphNetParams(hid, self.n_pts)
+        g_layers, a_layers = [], []
+        for _ in range(self.n_layers):
+            g_layers.append(_ResChebParams(hid, self.emd_dim, self._has_temb))
+            a_layers.append(_AttenLayerParams(hid, _clone(attn), _clone(ffn)))
+        self.gconv_input = gconv_input
+        self.gconv_layers = nn.ModuleList(g_layers)
+        self.atten_layers = nn.ModuleList(a_layers)
+        self.gconv_output = _ChebParams(hid, c_out)
+        self.temb = nn.Module()             # GCNpose carries an unused temb.dense as well (gcnpose.py:94-98)
+        self.temb.dense = nn.ModuleList([nn.Linear(hid, self.emd_dim), nn.Linear(self.emd_dim, self.emd_dim)])
+
+        self._c_in, self._c_out = c_in, c_out
+        self._handle = None
+        self._packed_version = None
+        self._engine = _lib.ENGINE_AUTO
+
+    def _out_dim(self):
+        return self.coords_dim[1]
+
+    # ---------------------------------------------------------------- checkpoint compatibility
+    def load_state_dict(self, state_dict, strict=True, **kw):
+        """Accepts reference checkpoints saved from a DataParallel wrapper (`module.` prefix)."""
+        if any(k.startswith("module.") for k in state_dict):
+            state_dict = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        out = super().load_state_dict(state_dict, strict=strict, **kw)
+        self._packed_version = None
+        return out
+
+    def set_engine(self, engine):
+        """'auto' | 'fp32' | 'tc' -- which kernel family runs the denoiser (see include/diffpose_b200.h)."""
+        self._engine = {"auto": _lib.ENGINE_AUTO, "fp32": _lib.ENGINE_FP32, "tc": _lib.ENGINE_TC}[engine]
+        if self._handle is not None:
+            _lib.check(_lib.load().dp_set_engine(self._handle, self._engine), "dp_set_engine")
+        return self
+
+    def engine(self):
+        self._ensure_packed(self._device())
+        return {1: "fp32", 2: "tc"}[_lib.load().dp_get_engine(self._handle)]
+
+    # ---------------------------------------------------------------- device state
+    def _device(self):
+        return self.gconv_input.weight.device
+
+    def _weights_version(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def _ensure_packed(self, device):
+        if device.type != "cuda":
+            raise RuntimeError("diffpose_nw_b200 runs on CUDA only (no CPU fallback): move the model and its inputs to a GPU")
+        lib = _lib.load()
+        if self._handle is None:
+            h = ctypes.c_void_p()
+            with torch.cuda.device(device):
+                _lib.check(lib.dp_create(ctypes.byref(h), self.n_pts, self._c_in, self._c_out, self.hid_dim,
+                                         self.n_layers, self.n_head, 1 if self._has_temb else 0), "dp_create")
+            self._handle = h
+            _lib.check(lib.dp_set_engine(h, self._engine), "dp_set_engine")
+        version = self._weights_version()
+        if version != self._packed_version:
+            sd = dict(self.named_parameters())
+            flat = torch.cat([sd[k].detach().reshape(-1).to(device=device, dtype=torch.float32)
+                              for k in _param_order(self.n_layers, self._has_temb)]).contiguous()
+            adj = torch.as_tensor(self.adj, dtype=torch.float32).detach().cpu().contiguous()
+            if tuple(adj.shape) != (self.n_pts, self.n_pts):
+                raise RuntimeError(f"adj must be [{self.n_pts},{self.n_pts}], got {tuple(adj.shape)}")
+            with torch.cuda.device(device):
+                stream = torch.cuda.current_stream(device).cuda_stream
+                _lib.check(lib.dp_pack(self._handle, flat.data_ptr(), flat.numel(), adj.data_ptr(), stream), "dp_pack")
+            self._packed_version = version
+
+    def _mask_bytes(self, mask, device):
+        if mask is None:
+            return None
+        m = mask.reshape(-1)
+        if m.numel() != self.n_pts:
+            raise RuntimeError(f"mask must have {self.n_pts} elements (reference passes [1,1,{self.n_pts}])")
+        return m.to(device=device, dtype=torch.uint8).contiguous()
+
+    def _check_x(self, x, c):
+        if not x.is_cuda:
+            raise RuntimeError("diffpose_nw_b200 runs on CUDA only (no CPU fallback): got a CPU tensor")
+        if x.dim() != 3 or x.shape[1] != self.n_pts or x.shape[2] != c:
+            raise RuntimeError(f"expected x of shape [n,{self.n_pts},{c}], got {tuple(x.shape)}")
+        return x.detach().to(torch.float32).contiguous()
+
+    def _forward(self, x, mask, t):
+        x = self._check_x(x, self._c_in)
+        dev = x.device
+        self._ensure_packed(dev)
+        n = x.shape[0]
+        out = torch.empty(n, self.n_pts, self._c_out, device=dev, dtype=torch.float32)
+        mb = self._mask_bytes(mask, dev)
+        tt = None
+        if self._has_temb:
+            tt = torch.as_tensor(t, device=dev).detach().to(torch.float32).reshape(-1).contiguous()
+            if tt.numel() != n:
+                raise RuntimeError(f"t must have one entry per sample ({n}), got {tt.numel()}")
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().dp_forward(self._handle, x.data_ptr(), tt.data_ptr() if tt is not None else None,
+                                              mb.data_ptr() if mb is not None else None, out.data_ptr(), n, stream),
+                       "dp_forward")
+        return out
+
+    def last_launch(self):
+        """(grid, block, smem_bytes, poses_per_tile, engine, n_tiles) of the last hot-path launch."""
+        buf = (ctypes.c_long * 6)()
+        _lib.check(_lib.load().dp_last_launch_info(self._handle, buf), "dp_last_launch_info")
+        return tuple(buf)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and _lib._lib is not None:
+                _lib._lib.dp_destroy(self._handle)
+                self._handle = None
+        except Exception:
+            pass
+
+
+class FusedGCNdiff(_FusedBase):
+    """GCNdiff(adj, config) -- the diffusion denoiser eps_theta(x_t, t)."""
+    _has_temb = True
+
+    def forward(self, x, mask, t, cemd=0):
+        """x [n,17,c_in] fp32 CUDA, mask [1,1,17] bool, t [n] -> eps [n,17,c_out].  `cemd` is ignored, as in the
+        reference (models/gcndiff.py:101)."""
+        return self._forward(x, mask, t)
+
+
+class FusedGCNpose(_FusedBase):
+    """GCNpose(adj, config) -- the stage-1 2D->3D lifter; output width is hard-coded to 3 (gcnpose.py:91)."""
+    _has_temb = False
+
+    def _out_dim(self):
+        return 3
+
+    def forward(self, x, mask):
+        return self._forward(x, mask, None)

@@ -1,0 +1,190 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the reference's golden outputs and the oracle.
+
+Tolerances.  north_star: final 3D joints within 1e-3 abs, MPJPE within 0.05 mm.
+  fp32 engine: every contraction is an fp32 FMA chain -> 2e-5 abs on eps (|eps| ~ 1-10) and on x (|x| ~ 1).
+  tensor-core engine: fp16 operands / fp32 accumulation -> the north_star tolerance (1e-3 abs on x).
+"""
+import numpy as np
+import pytest
+import torch
+
+import diffpose_nw_b200 as D
+from oracle import diffpose_oracle as O
+from _cases import DIFF_CASES, POSE_CASES, betas, build_diff, build_pose, mask_for, t
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+FP32_TOL = 2e-5
+TC_TOL_X = 1e-3
+
+
+def dev():
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    return torch.device("cuda:0")
+
+
+@pytest.mark.parametrize("tag", sorted(DIFF_CASES))
+def test_forward_fp32_vs_reference(golden, tag):
+    cfg, adj, model, sd = build_diff(tag, golden)
+    model = model.to(dev()).set_engine("fp32")
+    x, mask = t(golden, f"{tag}.x").to(dev()), mask_for(tag, golden).to(dev())
+    eps = model(x, mask, t(golden, f"{tag}.t").to(dev()), 0)
+    ref = t(golden, f"{tag}.eps")
+    assert eps.shape == ref.shape and eps.is_cuda
+    err = (eps.cpu() - ref).abs().max().item()
+    assert err < FP32_TOL * max(1.0, ref.abs().max().item()), f"{tag}: forward max|diff| {err:.3e}"
+
+
+@pytest.mark.parametrize("tag", sorted(DIFF_CASES))
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_sampler_vs_reference(golden, tag, engine):
+    cfg, adj, model, sd = build_diff(tag, golden)
+    model = model.to(dev()).set_engine(engine)
+    x, mask = t(golden, f"{tag}.x").to(dev()), mask_for(tag, golden).to(dev())
+    seq, eta = golden[f"{tag}.seq"].tolist(), float(golden[f"{tag}.eta"])
+    noise = t(golden, f"{tag}.noise").to(dev())
+    xs, x0 = D.generalized_steps(x, mask, seq, model, betas().to(dev()), eta=eta, noise=noise)
+    out = xs[-1]
+    ref = t(golden, f"{tag}.x_final")
+    tol = FP32_TOL if model.engine() == "fp32" else TC_TOL_X
+    err = (out.cpu() - ref).abs().max().item()
+    assert err < tol, f"{tag}/{model.engine()}: sampler max|diff| {err:.3e}"
+    assert xs[0] is x and x0 == []
+    # MPJPE of the xyz part against synthetic targets must agree within 0.05 mm
+    tgt = O.synthetic_targets(t(golden, f"{tag}.x"))
+    m_ref = O.mpjpe(O.root_centre(ref[:, :, 2:]), tgt).item() * 1000
+    m_out = O.mpjpe(O.root_centre(out.cpu()[:, :, 2:]), tgt).item() * 1000
+    assert abs(m_ref - m_out) < 0.05
+
+
+def test_sampler_return_all_matches_lists(golden):
+    cfg, adj, model, sd = build_diff("B", golden)
+    model = model.to(dev()).set_engine("fp32")
+    x, mask = t(golden, "B.x").to(dev()), mask_for("B", golden).to(dev())
+    xs, x0 = D.generalized_steps(x, mask, golden["B.seq"].tolist(), model, betas(), eta=float(golden["B.eta"]),
+                                 noise=t(golden, "B.noise").to(dev()), return_all=True)
+    assert len(xs) == 6 and len(x0) == 5
+    assert (xs[-1].cpu() - t(golden, "B.x_final")).abs().max().item() < FP32_TOL
+    assert (x0[-1].cpu() - t(golden, "B.x0_last")).abs().max().item() < 5e-5
+
+
+@pytest.mark.parametrize("tag", sorted(POSE_CASES))
+def test_gcnpose_vs_reference(golden, tag):
+    cfg, adj, model, sd = build_pose(tag, golden)
+    model = model.to(dev())
+    xyz = model(t(golden, f"{tag}.uv").to(dev()), torch.ones(1, 1, 17, dtype=torch.bool, device=dev()))
+    ref = t(golden, f"{tag}.xyz")
+    assert (xyz.cpu() - ref).abs().max().item() < FP32_TOL * max(1.0, ref.abs().max().item())
+
+
+def test_metrics_vs_reference(golden):
+    gt, pred = t(golden, "M.gt").to(dev()), t(golden, "M.pred").to(dev())
+    sums, pp = D.pose_error_sums(pred, gt, per_pose=True)
+    s = sums.cpu().numpy()
+    assert s[2] == 16
+    assert abs(s[0] / 16 - float(golden["M.mpjpe"])) < 1e-6
+    assert abs(s[1] / 16 - float(golden["M.p_mpjpe"])) < 1e-6
+    np.testing.assert_allclose(pp[:, 1].cpu().numpy(), golden["M.p_mpjpe_per_pose"], atol=1e-6)
+    # uvxyz layout (xyz at columns 2:5) gives the same numbers
+    pred5 = torch.cat([torch.zeros(16, 17, 2, device=dev()), pred], dim=2)
+    s5, _ = D.pose_error_sums(pred5, gt)
+    np.testing.assert_allclose(s5.cpu().numpy(), s, rtol=1e-12)
+    assert abs(D.mpjpe(pred, gt).item() - float(golden["M.mpjpe"])) < 1e-6
+    assert abs(D.p_mpjpe(pred, gt).item() - float(golden["M.p_mpjpe"])) < 1e-6
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_config2_shape_vs_oracle(engine):
+    """BASELINE config 1/2 shape (cpn.yml, seq [0,12], H=1) at a batch the oracle finishes in seconds; ragged tile."""
+    cfg = O.default_config()
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(adj, cfg)
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, seed=9)
+    model.load_state_dict(sd)
+    model = model.to(dev()).set_engine(engine)
+    n = 259                                      # not a multiple of any tile height
+    x = O.synthetic_poses(n, seed=4)
+    den = lambda xt, m, tt: O.gcndiff_forward(sd, adj, 5, 4, xt, m, tt)
+    ref = O.ddim_sample(x, None, [0, 12], den, betas(), eta=0.0)[0][-1]
+    out = D.generalized_steps(x.to(dev()), None, range(0, 24, 12), model, betas(), eta=0.0)[0][-1].cpu()
+    tol = FP32_TOL if model.engine() == "fp32" else TC_TOL_X
+    assert (out - ref).abs().max().item() < tol
+    tgt = O.synthetic_targets(x)
+    assert abs(O.mpjpe(O.root_centre(ref[:, :, 2:]), tgt).item() - O.mpjpe(O.root_centre(out[:, :, 2:]), tgt).item()) * 1000 < 0.05
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_hypotheses_mean_and_repeat(engine):
+    """config 3 semantics: H hypotheses, hypothesis-major layout, fused mean == mean of the unfused result;
+    kernel-side repeat == materialised `.repeat(H,1,1)`; eta = 0 makes hypotheses identical (quirk 3)."""
+    cfg = O.default_config()
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(adj, cfg)
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, seed=2)
+    model.load_state_dict(sd)
+    model = model.to(dev()).set_engine(engine)
+    B, H, seq = 37, 5, [0, 6]
+    x = O.synthetic_poses(B, seed=6).to(dev())
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(2, H * B, 17, 5, generator=g).to(dev())
+    xr = x.repeat(H, 1, 1)
+    full = D.sample(model, xr, None, seq, betas(), eta=1.0, noise=noise, n_hyp=H)
+    assert full.shape == (H * B, 17, 5)
+    fused = D.sample(model, x, None, seq, betas(), eta=1.0, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=True)
+    assert fused.shape == (B, 17, 5)
+    ref_mean = torch.mean(full.reshape(H, -1, 17, 5), 0)
+    assert (fused - ref_mean).abs().max().item() < 1e-6
+    # against the oracle, with the same noise
+    den = lambda xt, m, tt: O.gcndiff_forward(sd, adj, 5, 4, xt, m, tt)
+    ref = O.ddim_sample(xr.cpu(), None, seq, den, betas(), eta=1.0, noise=noise.cpu())[0][-1]
+    tol = FP32_TOL if model.engine() == "fp32" else TC_TOL_X
+    assert (full.cpu() - ref).abs().max().item() < tol
+    same = D.sample(model, xr, None, seq, betas(), eta=0.0, n_hyp=H)
+    assert torch.equal(same[:B], same[B:2 * B]) and torch.equal(same[:B], same[4 * B:])
+
+
+def test_edge_cases_and_errors():
+    cfg = O.default_config()
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev())
+    # empty batch returns an empty tensor
+    e = model(torch.zeros(0, 17, 5, device=dev()), None, torch.zeros(0, device=dev()), 0)
+    assert e.shape == (0, 17, 5)
+    s = D.generalized_steps(torch.zeros(0, 17, 5, device=dev()), None, [0, 12], model, betas())[0][-1]
+    assert s.shape == (0, 17, 5)
+    # single pose, single step
+    x1 = O.synthetic_poses(1).to(dev())
+    assert torch.isfinite(D.generalized_steps(x1, None, [0], model, betas())[0][-1]).all()
+    with pytest.raises(RuntimeError, match="shape"):
+        model(torch.zeros(2, 16, 5, device=dev()), None, torch.zeros(2, device=dev()), 0)
+    with pytest.raises(RuntimeError, match="one entry per sample"):
+        model(torch.zeros(2, 17, 5, device=dev()), None, torch.zeros(3, device=dev()), 0)
+    with pytest.raises(RuntimeError, match="multiple of n_hyp"):
+        D.sample(model, torch.zeros(7, 17, 5, device=dev()), None, [0, 12], betas(), n_hyp=2)
+    with pytest.raises(RuntimeError):
+        D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config(hid_dim=80)).to(dev())(x1, None, torch.zeros(1, device=dev()), 0)
+    # weights changed in place are re-packed
+    before = model(x1, None, torch.zeros(1, device=dev()), 0).clone()
+    with torch.no_grad():
+        model.gconv_output.bias.add_(1.0)
+    after = model(x1, None, torch.zeros(1, device=dev()), 0)
+    assert (after - before - 1.0).abs().max().item() < 1e-5
+
+
+def test_large_batch_properties():
+    """BASELINE config 2 full size (B=1024): size-independent properties instead of an oracle run --
+    batch-composition invariance (a pose's result does not depend on its neighbours or tile) and determinism."""
+    cfg = O.default_config()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev())
+    x = O.synthetic_poses(1024, seed=8).to(dev())
+    a = D.generalized_steps(x, None, range(0, 24, 12), model, betas())[0][-1]
+    b = D.generalized_steps(x, None, range(0, 24, 12), model, betas())[0][-1]
+    assert torch.equal(a, b)
+    perm = torch.randperm(1024, generator=torch.Generator().manual_seed(0)).to(dev())
+    c = D.generalized_steps(x[perm].contiguous(), None, range(0, 24, 12), model, betas())[0][-1]
+    assert (c - a[perm]).abs().max().item() < 1e-6
+    d = D.generalized_steps(x[:100].contiguous(), None, range(0, 24, 12), model, betas())[0][-1]
+    assert (d - a[:100]).abs().max().item() < 1e-6
+    assert D._lib.launch_count() > 0

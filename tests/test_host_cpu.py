@@ -1,0 +1,131 @@
+"""CPU: host-side mirror of the reference interface (no kernels run here)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import diffpose_nw_b200 as D
+from diffpose_nw_b200 import _lib
+from diffpose_nw_b200.model import _param_order
+from oracle import diffpose_oracle as O
+from _cases import betas
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_state_dict_layout_matches_reference():
+    # SURVEY.md 8a "state_dict layout": names, shapes, count
+    torch.manual_seed(0)
+    m = D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config())
+    sd = m.state_dict()
+    assert len(sd) == 123 and sum(v.numel() for v in sd.values()) == 1025674
+    expect = {
+        "gconv_input.weight": (3, 1, 5, 96), "gconv_input.bias": (1, 1, 96),
+        "gconv_layers.4.gconv2.gconv.weight": (3, 1, 96, 96), "gconv_layers.0.gconv1.gconv.bias": (1, 1, 96),
+        "gconv_layers.2.temb_proj.weight": (96, 384), "gconv_layers.2.temb_proj.bias": (96,),
+        "atten_layers.3.self_attn.linears.3.weight": (96, 96), "atten_layers.3.self_attn.linears.0.bias": (96,),
+        "atten_layers.0.feed_forward.A_hat": (17, 17), "atten_layers.0.feed_forward.gconv1.fc.weight": (192, 96),
+        "atten_layers.0.feed_forward.gconv2.fc.weight": (96, 192), "atten_layers.1.sublayer.1.norm.a_2": (96,),
+        "gconv_output.weight": (3, 1, 96, 5), "gconv_output.bias": (1, 1, 5),
+        "temb.dense.0.weight": (384, 96), "temb.dense.1.weight": (384, 384), "temb.dense.1.bias": (384,),
+    }
+    for k, shp in expect.items():
+        assert tuple(sd[k].shape) == shp, k
+    assert "adj" not in sd                      # adj is a plain attribute in the reference
+    assert sorted(_param_order(5, True)) == sorted(sd.keys())
+    # seeded init reproduces the reference constructor (SURVEY.md 8c known answer)
+    assert abs(sum(v.double().sum().item() for v in sd.values()) - 1124.303041338549) < 1e-9
+    np.testing.assert_allclose(sd["gconv_input.weight"][0, 0, 0, :3].numpy(), [-0.0363363251, -0.0371922664, -0.0080873892], rtol=1e-6)
+    # the reference deep-copies one attention block into every layer
+    assert torch.equal(sd["atten_layers.0.self_attn.linears.0.weight"], sd["atten_layers.4.self_attn.linears.3.weight"])
+
+
+def test_gcnpose_layout():
+    m = D.FusedGCNpose(D.adj_mx_from_edges(), O.default_config(coords_dim=[2, 3]))
+    sd = m.state_dict()
+    assert tuple(sd["gconv_input.weight"].shape) == (3, 1, 2, 96) and tuple(sd["gconv_output.weight"].shape) == (3, 1, 96, 3)
+    assert not any("temb_proj" in k for k in sd) and "temb.dense.0.weight" in sd
+    assert sum(v.numel() for v in sd.values()) == 839432
+
+
+def test_load_reference_style_checkpoint():
+    cfg = O.default_config()
+    torch.manual_seed(1)
+    src = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg)
+    ckpt = [{"module." + k: v.clone() for k, v in src.state_dict().items()}, {}, 3, 100]   # runner's list format
+    dst = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg)
+    dst.load_state_dict(ckpt[0])
+    assert all(torch.equal(a, b) for a, b in zip(src.state_dict().values(), dst.state_dict().values()))
+    with pytest.raises(RuntimeError):
+        dst.load_state_dict({"bogus": torch.zeros(1)})
+
+
+def test_ddim_steps_match_reference_scalars(golden):
+    for tag in ["A", "A1", "B", "D"]:
+        steps = D.ddim_steps(betas(), golden[f"{tag}.seq"].tolist(), float(golden[f"{tag}.eta"]))
+        sc = golden[f"{tag}.scalars"]
+        assert len(steps) == len(sc)
+        for s, row in zip(steps, sc):
+            tt, at, an, c1, c2 = row
+            assert s.t == tt and s.c1 == np.float32(c1) and s.c2 == np.float32(c2)
+            assert s.sqrt_at == np.sqrt(np.float32(at)) and s.sqrt_an == np.sqrt(np.float32(an))
+            assert s.sqrt_1m_at == np.sqrt(np.float32(1) - np.float32(at))
+    with pytest.raises(RuntimeError):
+        D.ddim_steps(betas(), range(0, 500, 10), 0.0)       # argv default 500 would index past the 51 betas
+
+
+def test_sequences_and_schedules(golden):
+    assert D.make_seq("uniform", 24, 2) == [0, 12] and D.make_seq("uniform", 50, 50) == list(range(50))
+    assert D.make_seq("quad", 24, 2) == O.eval_sequence("quad", 24, 2)
+    with pytest.raises(NotImplementedError):
+        D.make_seq("cosine", 24, 2)
+    for kind in ["linear", "quad", "const", "jsd", "sigmoid"]:
+        assert np.array_equal(D.get_beta_schedule(kind, beta_start=1e-4, beta_end=1e-3, num_diffusion_timesteps=51), golden[f"betas_{kind}"])
+    with pytest.raises(NotImplementedError):
+        D.get_beta_schedule("cosine", beta_start=1e-4, beta_end=1e-3, num_diffusion_timesteps=51)
+
+
+def test_no_cpu_fallback():
+    m = D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config(hid_dim=32, num_layer=1, n_head=2))
+    x = O.synthetic_poses(2)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        m(x, None, torch.zeros(2), 0)
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        D.generalized_steps(x, None, [0, 12], m, betas(), eta=0.0)
+    with pytest.raises(RuntimeError, match="FusedGCNdiff"):
+        D.generalized_steps(x, None, [0, 12], torch.nn.Linear(1, 1), betas())
+    with pytest.raises(RuntimeError, match="CUDA only"):
+        D.mpjpe(torch.zeros(1, 17, 3), torch.zeros(1, 17, 3))
+
+
+def test_shard_range_partitions():
+    for n in [0, 1, 7, 1024, 1000003]:
+        for w in [1, 2, 3, 8]:
+            spans = [D.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_abi_library_exports_header_symbols():
+    """The C-ABI library loads without a GPU and exports every function include/diffpose_b200.h declares."""
+    header = open(os.path.join(ROOT, "include", "diffpose_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(dp_[a-z_0-9]+)\s*\(", header))
+    assert {"dp_create", "dp_pack", "dp_forward", "dp_sample", "dp_metrics", "dp_destroy", "dp_last_error"} <= declared
+    assert declared == set(_lib.SIGNATURES), "binding table and header disagree"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), f"{name} missing from libdiffpose_b200.so"
+    lib.dp_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.dp_version()
+    assert ctypes.sizeof(_lib.DpStep) == 24
+    if not torch.cuda.is_available():
+        # without a device the library must fail loudly, not fall back
+        _lib.load()
+        h = ctypes.c_void_p()
+        rc = _lib.load().dp_create(ctypes.byref(h), 17, 5, 5, 96, 5, 4, 1)
+        assert rc != 0 and b"CUDA" in _lib.load().dp_last_error()
