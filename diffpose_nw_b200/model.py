@@ -228,6 +228,8 @@ class _FusedBase(nn.Module):
         self._ensure_packed(dev)
         n = x.shape[0]
         out = torch.empty(n, self.n_pts, self._c_out, device=dev, dtype=torch.float32)
+        if n == 0:
+            return out
         mb = self._mask_bytes(mask, dev)
         tt = None
         if self._has_temb:

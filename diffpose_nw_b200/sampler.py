@@ -118,6 +118,8 @@ def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_inpu
         nz = torch.randn(T, total, m.n_pts, m._c_in, device=dev, dtype=torch.float32)
     out_rows = n_pose if mean_over_hyp else total
     out = torch.empty(out_rows, m.n_pts, m._c_in, device=dev, dtype=torch.float32)
+    if total == 0:
+        return out
     mb = m._mask_bytes(src_mask, dev)
     with torch.cuda.device(dev):
         stream = torch.cuda.current_stream(dev).cuda_stream
