@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py -- poses/sec of full DDIM sampling (H hypotheses x T steps) through diffpose_nw_b200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cpn1024|sweep]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+           bench.py --gpus N --steps K --warmup W
+
+One "step" = one call of the hot path (`generalized_steps` -> dp_sample: all T DDIM steps of one batch in one
+persistent kernel) on one batch of synthetic Human3.6M-shaped poses.  Workload at every N (weak scaling: each rank
+processes its own batch): BASELINE.json configs[1] -- human36m_diffpose_uvxyz_cpn.yml shape, batch 1024, 1 hypothesis,
+seq = range(0,24,12) (T = 2), random-init weights.  Prints ONE JSON line on rank 0.
+
+  value      device-timed throughput, inputs already resident in HBM (rotating through a pool larger than L2)
+  e2e        same metric through the public API with pinned HOST buffers: H2D of x and D2H of x_T inside the timed region
+  roofline   tensor bound: algorithmic FLOPs (24.65 MFLOP per pose-forward) / dp_sample device time
+  cpu_baseline  the oracle port (PyTorch CPU restatement of the reference) timed on the host cores, bounded sample
+  --impl reference   the reference's CPU implementation of the path (oracle port; the reference is pure Python and
+                     /root/reference does not exist on the GPU box) on all host threads, same config/metric.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_POSE_FORWARD = 24.65e6          # minimal algorithmic work, SURVEY.md section 8d
+ROW_BYTES = 17 * 5 * 4                   # one uvxyz pose, fp32
+METRIC = "poses/sec, full DDIM sampling (H hyps x T steps)"
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: cpn.yml shape, batch 1024, H=1, config eval timesteps (2 of 24)
+    "cpn1024": dict(batch=1024, n_hyp=1, seq=list(range(0, 24, 12)), eta=0.0,
+                    name="configs[1]: human36m_diffpose_uvxyz_cpn.yml shape, batch 1024, H=1, seq=[0,12] (T=2), random-init"),
+    # a slice of BASELINE.json configs[3] (1M x 10 x 50 sweep): same H and T, 16384 poses per step
+    "sweep": dict(batch=16384, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
+                  name="slice of configs[3]: 16384 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(tflops=float(d.get("bf16_tflops", 1590.0)), hbm=float(d.get("hbm_gbs", 6650.0)), src="measured (MEASURED_PEAKS.json, bf16 burst)")
+    return dict(tflops=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the benchmark runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.t0, self.t1 = [], None, None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), line.strip()))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        inside = [r for (ts, r) in self.rows if self.t0 is not None and self.t0 - 0.05 <= ts <= self.t1 + 0.1]
+        rows = inside or [r for (_, r) in self.rows]
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [c.strip() for c in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); pw.append(float(f[2]))
+            except Exception:
+                continue
+            for nme, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nme)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm), "in_timed_region": bool(inside), "power_w_max": max(pw) if pw else None}
+
+
+def oracle_setup(wl, n):
+    """Weights/inputs for the CPU legs: same architecture, seeds and synthetic distribution as the GPU arm."""
+    import torch
+    import diffpose_nw_b200 as D
+    from oracle import diffpose_oracle as O
+    cfg = O.default_config()
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    sd = {k: v.detach().clone() for k, v in D.FusedGCNdiff(adj, cfg).state_dict().items()}
+    betas = torch.from_numpy(O.beta_schedule("linear", 1e-4, 1e-3, 51)).float()
+    x = O.synthetic_poses(n, seed=1).repeat(wl["n_hyp"], 1, 1)
+    den = lambda xt, m, tt: O.gcndiff_forward(sd, adj, 5, 4, xt, m, tt)
+    mask = torch.ones(1, 1, 17, dtype=torch.bool)
+    run = lambda: O.ddim_sample(x, mask, wl["seq"], den, betas, eta=wl["eta"])[0][-1]
+    return run
+
+
+def time_oracle(wl, n, budget_s, min_reps=2):
+    import torch
+    torch.set_num_threads(os.cpu_count() or 1)
+    run = oracle_setup(wl, n)
+    with torch.no_grad():
+        run()
+        reps, t0 = 0, time.perf_counter()
+        while reps < min_reps or time.perf_counter() - t0 < budget_s:
+            run()
+            reps += 1
+        dt = time.perf_counter() - t0
+    return n * reps / dt, reps, dt
+
+
+def run_reference(args, wl):
+    """The reference arm: the reference's CPU implementation of the path (oracle port), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    steps, warm = args.steps, args.warmup
+    # size the per-step sample so the whole run stays within ~2 minutes
+    probe_n = 32
+    rate, _, _ = time_oracle(wl, probe_n, 1.0, min_reps=1)
+    per_step = 110.0 / max(1, steps + warm)
+    n = int(max(8, min(wl["batch"], rate * per_step)))
+    run = oracle_setup(wl, n)
+    with torch.no_grad():
+        for _ in range(warm):
+            run()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            run()
+        dt = time.perf_counter() - t0
+    val = n * steps / dt
+    sample = f"{n}-pose slice of the {wl['batch']}-pose batch per step, H={wl['n_hyp']}, T={len(wl['seq'])}, {steps} steps after {warm} warm-up"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "poses/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": wl["name"], "batch": wl["batch"], "n_hyp": wl["n_hyp"], "T": len(wl["seq"]),
+                                            "device": "host CPU", "torch_threads": torch.get_num_threads()},
+            "cpu_baseline": {"value": val, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cpn1024", choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args, wl)
+
+    import torch
+    import diffpose_nw_b200 as D
+    from diffpose_nw_b200 import _lib
+    from oracle import diffpose_oracle as O   # synthetic input generators + the cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a GPU (the product has no CPU path); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    torch.set_grad_enabled(False)
+
+    B, H, seq, eta = wl["batch"], wl["n_hyp"], wl["seq"], wl["eta"]
+    T = len(seq)
+    cfg = O.default_config()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev).set_engine(args.engine)
+    betas = torch.from_numpy(D.get_beta_schedule("linear", beta_start=1e-4, beta_end=1e-3, num_diffusion_timesteps=51)).float()
+    steps_arr = D.ddim_steps(betas, seq, eta)
+
+    # input pool larger than L2 so every timed step reads inputs that are not cache resident
+    l2_bytes = 126 * 1024 * 1024
+    batch_bytes = B * ROW_BYTES
+    pool_n = max(2, min(args.steps + args.warmup, (int(l2_bytes * 1.1) + batch_bytes - 1) // batch_bytes))
+    base = O.synthetic_poses(B, seed=1 + rank)
+    g = torch.Generator().manual_seed(100 + rank)
+    pool = (base[None] + 0.01 * torch.randn(pool_n, 1, 17, 5, generator=g)).to(dev).contiguous()
+    pool[:, :, 0, 2:] = 0
+    noise = None
+    if eta > 0:
+        noise = torch.randn(T, B * H, 17, 5, device=dev)
+    targets = O.synthetic_targets(base).to(dev)
+
+    def step(i):
+        return D.sample(model, pool[i % pool_n], None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True,
+                        mean_over_hyp=(H > 1), steps=steps_arr)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    for i in range(args.warmup):
+        out = step(args.steps + i)
+    barrier()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if sampler:
+        sampler.t0 = time.time()
+    ev0.record()
+    for i in range(args.steps):
+        out = step(i)
+    ev1.record()
+    barrier()
+    if sampler:
+        sampler.t1 = time.time()
+    launches = _lib.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * B * args.steps / (ms * 1e-3)
+
+    # ---- end-to-end: pinned host buffers, H2D + D2H inside the timed region, public API
+    host_in = [torch.empty(B, 17, 5).pin_memory() for _ in range(2)]
+    host_in[0].copy_(base); host_in[1].copy_(base)
+    out_rows = B if H > 1 else B * H
+    host_out = [torch.empty(out_rows, 17, 5).pin_memory() for _ in range(2)]
+    xd = torch.empty(B, 17, 5, device=dev)
+
+    def e2e_step(i):
+        xd.copy_(host_in[i & 1], non_blocking=True)
+        o = D.sample(model, xd, None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=(H > 1), steps=steps_arr)
+        host_out[i & 1].copy_(o, non_blocking=True)
+
+    e_steps = max(3, min(args.steps, 200))
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e_steps):
+        e2e_step(i)
+    torch.cuda.synchronize()
+    e_ms = (time.perf_counter() - t0) * 1e3
+    if dist is not None:
+        tms = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        e_ms = float(tms.item())
+    e2e_value = world * B * e_steps / (e_ms * 1e-3)
+    assert torch.isfinite(host_out[0]).all()
+
+    # ---- the evaluation tail: per-rank partial sums + one all-reduce (NCCL) -- not part of the timed sampler region
+    sums, _ = D.pose_error_sums(out, targets)
+    mp, pmp, cnt = D.reduce_metrics(sums)
+    clocks = sampler.stop() if sampler else None
+
+    if rank == 0:
+        peaks = load_peaks()
+        per_launch_s = ms * 1e-3 / args.steps
+        flops = B * H * T * FLOP_PER_POSE_FORWARD
+        achieved = flops / per_launch_s / 1e12
+        hbm_bytes = B * ROW_BYTES + out_rows * ROW_BYTES + (T * B * H * ROW_BYTES if noise is not None else 0)
+        ll = model.last_launch()
+        line = {
+            "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (tcgen05)" if model.engine() == "tc" else "f32",
+            "data": "synthetic",
+            "config": {"workload": wl["name"], "batch_per_gpu": B, "n_hyp": H, "T": T, "eta": eta, "engine": model.engine(),
+                       "l2": f"inputs rotate through a {pool_n * batch_bytes / 2**20:.0f} MiB pool (> 126 MiB L2) when steps+warmup >= {pool_n}; "
+                             "weights stay L2-resident by design",
+                       "launch": {"grid": ll[0], "block": ll[1], "smem": ll[2], "poses_per_tile": ll[3], "tiles": ll[5]}},
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": B * ROW_BYTES, "d2h_bytes_per_step": out_rows * ROW_BYTES,
+                    "steps": e_steps, "ms_per_step": e_ms / e_steps},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                         "traffic": None, "peak_source": peaks["src"],
+                         "note": "achieved = 24.65 MFLOP x poses x H x T per dp_sample / mean device time of dp_sample (temb prologue + persistent kernel)",
+                         "hbm_gbs": hbm_bytes / per_launch_s / 1e9},
+            "clocks": clocks,
+            "eval": {"mpjpe_mm": mp, "p_mpjpe_mm": pmp, "poses": cnt},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            n_cpu = 256 if H * T <= 4 else 16
+            v, reps, dt = time_oracle(wl, n_cpu, 12.0)
+            line["cpu_baseline"] = {"value": v, "unit": "poses/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": f"{n_cpu}-pose slice of the workload (H={H}, T={T}), {reps} reps in {dt:.1f} s after 1 warm-up, torch CPU threads={os.cpu_count()}"}
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
