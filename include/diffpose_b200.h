@@ -119,6 +119,11 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
 int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                double* sums, float* per_pose, void* stream);
 
+/* Diagnostic: one 128x96x96 tensor-core product through the engine's own operand layouts, descriptors, TMA weight
+ * staging and TMEM read-back: d[128][96] = fp16(a[128][96]) * fp16(w_kn[96][96]) + bias[96] (fp32 accumulate).
+ * All pointers are device fp32; synchronises the stream.  Used by the GPU tests to isolate layout bugs. */
+int dp_selftest_umma(const float* a, const float* w_kn, const float* bias, float* d, void* stream);
+
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long dp_launch_count(void);
 
