@@ -47,15 +47,16 @@ constexpr int OFF_ONES = OFF_A + 3 * ABLK_BYTES;           // 125504
 constexpr int OFF_W = (OFF_ONES + ONES_BYTES + 127) / 128 * 128;  // 129664
 constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // 215744: x_t [128][8] fp32
 constexpr int OFF_EP = OFF_XT + TM * 8 * 4;                // 219840: eps [128][8] fp32
-constexpr int OFF_NBI = OFF_EP + TM * 8 * 4;               // 223936: neighbour index  [17][9] int
-constexpr int OFF_NBC = OFF_NBI + NP * NNB * 4;            //         neighbour coeffs [17][9] float2 (T1, T2)
-constexpr int OFF_LH = OFF_NBC + NP * NNB * 8;             //         Lhat [17][17]
-constexpr int OFF_MASK = OFF_LH + 1168;                    //         key mask [32]
-constexpr int OFF_BAR = OFF_MASK + 128;                    //         mbarriers: full[4], empty[4], mma_done
+constexpr int al16(int x) { return (x + 15) / 16 * 16; }
+constexpr int OFF_NBI = OFF_EP + TM * 8 * 4;               // neighbour index  [17][9] int
+constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
+constexpr int OFF_LH = al16(OFF_NBC + NP * NNB * 8);       // Lhat [17][17]
+constexpr int OFF_MASK = al16(OFF_LH + NP * NP * 4);       // key mask [32]
+constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], mma_done
 constexpr int OFF_TMEM = OFF_BAR + 128;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 128 == 0 && OFF_A % 128 == 0 && OFF_ONES % 16 == 0, "alignment");
+static_assert(OFF_W % 128 == 0 && OFF_A % 128 == 0 && OFF_ONES % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0, "alignment");
 static_assert(TR * XLD * 4 <= 2 * ABLK_BYTES, "fp32 scratch rows must not reach operand block 2");
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
