@@ -51,7 +51,8 @@ constexpr int al16(int x) { return (x + 15) / 16 * 16; }
 constexpr int OFF_NBI = OFF_EP + TM * 8 * 4;               // neighbour index  [17][9] int
 constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
 constexpr int OFF_LH = al16(OFF_NBC + NP * NNB * 8);       // Lhat [17][17]
-constexpr int OFF_MASK = al16(OFF_LH + NP * NP * 4);       // key mask [32]
+constexpr int OFF_TE = al16(OFF_LH + NP * NP * 4);         // temb of the current (step, layer) [96]
+constexpr int OFF_MASK = OFF_TE + H * 4;                   // key mask [32]
 constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], mma_done
 constexpr int OFF_TMEM = OFF_BAR + 128;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
@@ -76,6 +77,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "@p bra WAIT_DONE;\n\t"
       "bra WAIT_LOOP;\n\t"
       "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// waits with back-off: for the producer, which is almost always waiting and must not steal issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) break;
+    __nanosleep(256);
+  }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
@@ -210,7 +221,7 @@ __device__ __forceinline__ void epilogue(uint8_t* smem, uint32_t tmem_base, cons
     if (KIND == EPI_RELU_TEMB_F16) {
 #pragma unroll
       for (int i = 0; i < 16; i += 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(temb + c + i));
+        const float4 t = *reinterpret_cast<const float4*>(temb + c + i);
         v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
       }
     }
@@ -245,30 +256,42 @@ __device__ __forceinline__ void wait_gemm(Pipe& p) {
   tc_fence_after();
 }
 
-// LayerNorm of the residual stream (GraFormer.py:67-70), one warp per row, 24 lanes x 4 channels.
-// TO_F16: write the fp16 operand block `blk`; else write fp32 rows (stride XLD) at OFF_A.
+// LayerNorm of the residual stream (GraFormer.py:67-70): lanes (2r, 2r+1) own the two 48-channel halves of row r.
+// TO_F16: write the fp16 operand block `blk` (all 128 rows); else write fp32 rows (stride XLD) at OFF_A (valid rows).
 template <bool TO_F16>
 __device__ __forceinline__ void layer_norm_tile(uint8_t* smem, int blk, const float* __restrict__ ga, const float* __restrict__ gb) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const float* X = reinterpret_cast<const float*>(smem + OFF_X);
-  float4 a = make_float4(0, 0, 0, 0), b = a;
-  if (lane < 24) { a = __ldg(reinterpret_cast<const float4*>(ga) + lane); b = __ldg(reinterpret_cast<const float4*>(gb) + lane); }
-  for (int r = warp; r < (TO_F16 ? TM : TR); r += 8) {
-    float4 v = make_float4(0, 0, 0, 0);
-    if (lane < 24) v = *reinterpret_cast<const float4*>(X + r * XLD + lane * 4);
-    const float mean = warp_sum(v.x + v.y + v.z + v.w) / (float)H;
-    float4 d = make_float4(v.x - mean, v.y - mean, v.z - mean, v.w - mean);
-    float q = (lane < 24) ? (d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w) : 0.f;
-    const float den = sqrtf(warp_sum(q) / (float)(H - 1)) + 1e-6f;
-    if (lane < 24) {
-      const float o0 = (a.x * d.x) / den + b.x, o1 = (a.y * d.y) / den + b.y, o2 = (a.z * d.z) / den + b.z, o3 = (a.w * d.w) / den + b.w;
-      if (TO_F16) {
-        uint2 pk = make_uint2(pack2(o0, o1), pack2(o2, o3));
-        *reinterpret_cast<uint2*>(smem + OFF_A + blk * ABLK_BYTES + a_chunk(r, lane >> 1) + (lane & 1) * 8) = pk;
-      } else {
-        *reinterpret_cast<float4*>(reinterpret_cast<float*>(smem + OFF_A) + r * XLD + lane * 4) = make_float4(o0, o1, o2, o3);
-      }
-    }
+  const int row = threadIdx.x >> 1, hh = threadIdx.x & 1;
+  const float* xr = reinterpret_cast<const float*>(smem + OFF_X) + row * XLD + hh * 48;
+  float v[48];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const float4 u = *reinterpret_cast<const float4*>(xr + 4 * q);
+    v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 48; ++i) s += v[i];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  const float mean = s * (1.0f / (float)H);
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 48; ++i) { v[i] -= mean; q2 = fmaf(v[i], v[i], q2); }
+  q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+  const float inv = 1.0f / (sqrtf(q2 * (1.0f / (float)(H - 1))) + 1e-6f);
+  if (!TO_F16 && row >= TR) return;
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(ga + hh * 48) + q), b = __ldg(reinterpret_cast<const float4*>(gb + hh * 48) + q);
+    v[4 * q] = fmaf(a.x * inv, v[4 * q], b.x); v[4 * q + 1] = fmaf(a.y * inv, v[4 * q + 1], b.y);
+    v[4 * q + 2] = fmaf(a.z * inv, v[4 * q + 2], b.z); v[4 * q + 3] = fmaf(a.w * inv, v[4 * q + 3], b.w);
+  }
+  if (TO_F16) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) *reinterpret_cast<uint4*>(smem + OFF_A + blk * ABLK_BYTES + a_chunk(row, hh * 6 + c)) = pack8(v + 8 * c);
+  } else {
+    float* y = reinterpret_cast<float*>(smem + OFF_A) + row * XLD + hh * 48;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) *reinterpret_cast<float4*>(y + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
 }
 
@@ -279,7 +302,7 @@ __device__ __forceinline__ void attention_tile(uint8_t* smem, int npose) {
   const uint8_t* Q = smem + OFF_A;
   const uint8_t* K = Q + ABLK_BYTES;
   const uint8_t* V = K + ABLK_BYTES;
-  const float scale = sqrtf(24.0f);
+  const float scale = 1.0f / sqrtf(24.0f);
   const int per_head = npose * NP;
   for (int task = threadIdx.x; task < 4 * per_head; task += kComputeThreads) {
     const int h = task / per_head, rr = task - h * per_head;   // rr = pose*17 + joint = tile row
@@ -300,7 +323,7 @@ __device__ __forceinline__ void attention_tile(uint8_t* smem, int npose) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) s = fmaf(q[8 * c + e], kv[e], s);
       }
-      s = s / scale;
+      s = s * scale;
       if (maskf[j] == 0.f) s = -1e9f;
       sc[j] = s;
       mx = fmaxf(mx, s);
@@ -497,7 +520,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(TcArgs a, StepsArg inl)
       for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int step = 0; step < a.n_steps; ++step)
           for (int blk = 0; blk < L * BLOCKS_PER_LAYER; ++blk) {
-            mbar_wait(pp.empty0 + 8 * stage, phase ^ 1);
+            mbar_wait_sleep(pp.empty0 + 8 * stage, phase ^ 1);
             mbar_expect_tx(pp.full0 + 8 * stage, WBLK_BYTES);
             bulk_g2s(sbase + OFF_W + stage * WBLK_BYTES, a.wpack + (size_t)blk * WBLK_BYTES, WBLK_BYTES, pp.full0 + 8 * stage);
             if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
@@ -568,6 +591,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(TcArgs a, StepsArg inl)
         for (int l = 0; l < L; ++l) {
           const LayerW& Lw = w.layer[l];
           for (int i = tid; i < NP * NP; i += kComputeThreads) lh[i] = __ldg(Lw.lhat + i);
+          if (tid < H) reinterpret_cast<float*>(smem + OFF_TE)[tid] = __ldg(a.temb + ((size_t)step * L + l) * H + tid);
           // ======== x = x + attn(LN0(x))
           layer_norm_tile<true>(smem, 2, Lw.ln0_a, Lw.ln0_b);
           publish_operand();
@@ -630,7 +654,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc_kernel(TcArgs a, StepsArg inl)
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          epilogue<96, EPI_RELU_TEMB_F16>(smem, tmem_base, a.temb + ((size_t)step * L + l) * H);
+          epilogue<96, EPI_RELU_TEMB_F16>(smem, tmem_base, reinterpret_cast<const float*>(smem + OFF_TE));
           tc_fence_before();
           bar_compute();
           cheb_concat_tile<false>(smem);
