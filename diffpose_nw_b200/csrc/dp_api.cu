@@ -250,6 +250,7 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DP_TRY(pack_fp32(h, params, adj_host, s));
   if (tc_supported(h->d)) DP_TRY(tc_pack(h, s));
+  h->temb_t.clear();
   h->packed = true;
   return DP_OK;
 }
@@ -279,6 +280,7 @@ int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char*
   if (n == 0) return DP_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // Per-sample timesteps need a per-sample embedding table; the fp32 engine serves this entry point.
+  h->temb_t.clear();   // the table buffer is about to be reused for per-sample rows
   return simt_forward(h, x, t, mask, out, n, s);
 }
 
@@ -309,8 +311,17 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
     DP_CUDA(cudaStreamSynchronize(s));
     steps_dev = h->steps;
   }
-  // batch-invariant time embeddings: one row per step (models/gcndiff.py:103-106, :51)
-  DP_TRY(simt_temb(h, steps_dev ? &steps_dev->t : nullptr, sizeof(dp_step) / sizeof(float), &inl, n_steps, s));
+  // batch-invariant time embeddings: one row per step (models/gcndiff.py:103-106, :51).  The table depends only
+  // on the weights and the schedule, so it is kept across calls until either changes.
+  {
+    bool same = (long)h->temb_t.size() == n_steps;
+    for (int i = 0; same && i < n_steps; ++i) same = (h->temb_t[i] == steps_host[i].t);
+    if (!same) {
+      DP_TRY(simt_temb(h, steps_dev ? &steps_dev->t : nullptr, sizeof(dp_step) / sizeof(float), &inl, n_steps, s));
+      h->temb_t.resize(n_steps);
+      for (int i = 0; i < n_steps; ++i) h->temb_t[i] = steps_host[i].t;
+    }
+  }
 
   float* dst = x_out;
   const int row_floats = d.n_pts * d.c_out;

@@ -93,6 +93,7 @@ struct dp_model {
 
   float* temb = nullptr;          // [n_rows][n_layer][hid] time-embedding table scratch
   size_t temb_cap = 0;            // capacity in floats
+  std::vector<float> temb_t;      // timesteps the table currently holds (sampler schedule cache; empty = invalid)
   dp_step* steps = nullptr;       // device copy of the step scalars, only used when n_steps > kMaxInlineSteps
   size_t steps_cap = 0;
   float* hyp_scratch = nullptr;   // [n_pose*n_hyp, n_pts, c] when the hypothesis mean is fused after sampling

@@ -380,6 +380,7 @@ __global__ void temb_kernel(const Weights* wp, Dims d, const float* __restrict__
     float acc[kTB];
 #pragma unroll
     for (int b = 0; b < kTB; ++b) acc[b] = __ldg(w.bd0 + n);
+#pragma unroll 8
     for (int k = 0; k < H; ++k) {
       const float wv = __ldg(w.wd0 + (size_t)k * E + n);
 #pragma unroll
@@ -393,6 +394,7 @@ __global__ void temb_kernel(const Weights* wp, Dims d, const float* __restrict__
     float acc[kTB];
 #pragma unroll
     for (int b = 0; b < kTB; ++b) acc[b] = __ldg(w.bd1 + n);
+#pragma unroll 8
     for (int k = 0; k < E; ++k) {
       const float wv = __ldg(w.wd1 + (size_t)k * E + n);
 #pragma unroll
@@ -408,6 +410,7 @@ __global__ void temb_kernel(const Weights* wp, Dims d, const float* __restrict__
     float acc[kTB];
 #pragma unroll
     for (int b = 0; b < kTB; ++b) acc[b] = __ldg(L.bt + n);
+#pragma unroll 8
     for (int k = 0; k < E; ++k) {
       const float wv = __ldg(L.wt + (size_t)k * H + n);
 #pragma unroll

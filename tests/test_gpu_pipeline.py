@@ -1,0 +1,71 @@
+"""GPU (-m gpu): the evaluation pipeline around the sampler (body of test_hyber, runners/diffpose_frame.py:330-391):
+BASELINE configs[4] semantics -- GCNpose lift, out-of-place root-centring, concat, H hypotheses, DDIM, hypothesis mean,
+MPJPE / P-MPJPE partial sums -- against the oracle on a small batch; plus shard-equals-whole."""
+import numpy as np
+import pytest
+import torch
+
+import diffpose_nw_b200 as D
+from oracle import diffpose_oracle as O
+from _cases import betas
+
+pytestmark = pytest.mark.gpu
+torch.set_grad_enabled(False)
+
+
+def _models():
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    diff = D.FusedGCNdiff(adj, O.default_config())
+    sd_d = O.perturb_state_dict({k: v.detach().clone() for k, v in diff.state_dict().items()}, seed=21, scale=0.02)
+    diff.load_state_dict(sd_d)
+    torch.manual_seed(1)
+    pose = D.FusedGCNpose(adj, O.default_config(coords_dim=[2, 3]))
+    sd_p = O.perturb_state_dict({k: v.detach().clone() for k, v in pose.state_dict().items()}, seed=22, scale=0.02)
+    pose.load_state_dict(sd_p)
+    return adj, diff, sd_d, pose, sd_p
+
+
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+def test_two_stage_pipeline_vs_oracle(engine):
+    dev = torch.device("cuda:0")
+    adj, diff, sd_d, pose, sd_p = _models()
+    diff, pose = diff.to(dev).set_engine(engine), pose.to(dev)
+    B, Hh, seq, eta = 23, 5, [0, 6], 1.0
+    uv = O.synthetic_poses(B, seed=30)[:, :, :2].contiguous()
+    tgt = O.synthetic_targets(O.synthetic_poses(B, seed=30), seed=31)
+    g = torch.Generator().manual_seed(32)
+    noise = torch.randn(len(seq), Hh * B, 17, 5, generator=g)
+    mask = torch.ones(1, 1, 17, dtype=torch.bool)
+    # oracle: the runner's glue restated with the intended (out-of-place) root-centring
+    xyz = O.root_centre(O.gcnpose_forward(sd_p, adj, 5, 4, uv, mask))
+    x = torch.cat([uv, xyz], dim=2).repeat(Hh, 1, 1)
+    den = lambda xt, m, tt: O.gcndiff_forward(sd_d, adj, 5, 4, xt, m, tt)
+    ref = O.hypothesis_mean(O.ddim_sample(x, mask, seq, den, betas(), eta=eta, noise=noise)[0][-1], Hh)
+    ref_xyz = O.root_centre(ref[:, :, 2:])
+    want = (O.mpjpe(ref_xyz, O.root_centre(tgt)).item() * 1000, float(O.p_mpjpe_per_pose(ref_xyz.numpy(), O.root_centre(tgt).numpy()).mean()) * 1000)
+    # product
+    out = D.lift_and_refine(diff, model_pose=pose, input_2d=uv.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(),
+                            eta=eta, test_times=Hh, noise=noise.to(dev))
+    tol = 2e-5 if diff.engine() == "fp32" else 1e-3
+    assert (out.cpu() - ref).abs().max().item() < tol
+    sums = D.evaluate_shard(diff, None, tgt.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(), eta=eta, test_times=Hh,
+                            noise=noise.to(dev), model_pose=pose, input_2d=uv.to(dev), batch_size=10)
+    m, pm, cnt = D.reduce_metrics(sums)
+    assert cnt == B and abs(m - want[0]) < 0.05 and abs(pm - want[1]) < 0.05
+
+
+def test_shards_equal_whole():
+    """Sharding over ranks never changes a pose's result: the union of 3 contiguous shards equals the unsharded run."""
+    dev = torch.device("cuda:0")
+    adj, diff, sd_d, _, _ = _models()
+    diff = diff.to(dev)
+    n, Hh, seq = 50, 2, [0, 12]
+    x = O.synthetic_poses(n, seed=40).to(dev)
+    tgt = O.synthetic_targets(x.cpu(), seed=41).to(dev)
+    whole = D.evaluate_shard(diff, x, tgt, seq=seq, betas=betas(), test_times=Hh)
+    parts = torch.zeros(3, device=dev, dtype=torch.float64)
+    for r in range(3):
+        lo, hi = D.shard_range(n, r, 3)
+        parts += D.evaluate_shard(diff, x[lo:hi].contiguous(), tgt[lo:hi].contiguous(), seq=seq, betas=betas(), test_times=Hh)
+    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=1e-9)
