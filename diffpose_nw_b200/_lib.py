@@ -18,6 +18,10 @@ class DpStep(ctypes.Structure):
                 ("sqrt_an", ctypes.c_float), ("c1", ctypes.c_float), ("c2", ctypes.c_float)]
 
 
+class DpMmaOp(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_uint) for n in ("a_off", "a_lbo", "a_sbo", "b_off", "b_lbo", "b_sbo", "idesc", "tmem_col", "accumulate")]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check every header symbol is exported
 _P, _I, _L = ctypes.c_void_p, ctypes.c_int, ctypes.c_long
 SIGNATURES = {
@@ -29,7 +33,7 @@ SIGNATURES = {
     "dp_forward": (_I, [_P, _P, _P, _P, _P, _L, _P]),
     "dp_sample": (_I, [_P, _P, _I, _P, _L, _I, ctypes.POINTER(DpStep), _I, _P, _P, _I, _P]),
     "dp_metrics": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P]),
-    "dp_selftest_umma": (_I, [_P, _P, _P, _P, _P]),
+    "dp_selftest_umma": (_I, [_P, _I, _P, _I, _P, _I, _P]),
     "dp_launch_count": (_L, []),
     "dp_last_launch_info": (_I, [_P, ctypes.POINTER(_L)]),
     "dp_last_error": (ctypes.c_char_p, []),

@@ -348,9 +348,10 @@ int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float*
   return metrics_launch(pred, pred_stride, pred_offset, gt, n, n_pts, sums, per_pose, static_cast<cudaStream_t>(stream));
 }
 
-int dp_selftest_umma(const float* a, const float* w_kn, const float* bias, float* d, void* stream) {
-  DP_REQUIRE(a && w_kn && bias && d, "dp_selftest_umma: NULL argument");
-  return tc_selftest(a, w_kn, bias, d, static_cast<cudaStream_t>(stream));
+int dp_selftest_umma(const void* smem_image, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols,
+                     void* stream) {
+  DP_REQUIRE(smem_image && ops_host && tmem_out, "dp_selftest_umma: NULL argument");
+  return tc_lab(smem_image, image_bytes, ops_host, n_ops, tmem_out, ncols, static_cast<cudaStream_t>(stream));
 }
 
 long dp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

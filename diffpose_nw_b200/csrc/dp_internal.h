@@ -120,7 +120,7 @@ void tc_free(dp_model* m);
 int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
               const unsigned char* mask, cudaStream_t s);
-int tc_selftest(const float* A, const float* Wkn, const float* bias, float* D, cudaStream_t s);
+int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* out_dev, int ncols, cudaStream_t s);
 // dp_metrics.cu
 int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                    double* sums, float* per_pose, cudaStream_t s);

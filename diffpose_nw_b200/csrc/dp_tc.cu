@@ -753,55 +753,52 @@ __global__ void tc_pack_block_kernel(uint8_t* __restrict__ dst, const float* __r
   }
 }
 
-// ---- UMMA self test: D[128][96] = A[128][96] * W[96][96]^T + bias through the same layouts / descriptors / TMEM path
-__global__ void __launch_bounds__(128, 1) tc_selftest_kernel(const float* __restrict__ A, const uint8_t* __restrict__ wblk, float* __restrict__ D) {
+// ---- UMMA lab: run a caller-described list of tcgen05.mma instructions over a caller-built shared-memory image and
+// dump TMEM.  The GPU tests use it to pin down every operand flavour the engine relies on (K-major / MN-major A and B,
+// custom leading-dimension offsets, N = 32/64/96/128) against numpy.
+__global__ void __launch_bounds__(128, 1) tc_lab_kernel(const uint8_t* __restrict__ image, int image_bytes, const dp_mma_op* __restrict__ ops,
+                                                        int n_ops, float* __restrict__ out, int ncols) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5;
   const uint32_t sbase = smem_u32(smem);
-  const uint32_t full = sbase + OFF_BAR, done = sbase + OFF_BAR + 64;
-  if (tid == 0) { mbar_init(full, 1); mbar_init(done, 1); fence_mbar_init(); }
+  const int off_bar = (image_bytes + 15) / 16 * 16;
+  const uint32_t done = sbase + off_bar;
+  if (tid == 0) { mbar_init(done, 1); fence_mbar_init(); }
   __syncwarp();
-  if (warp == 0) tmem_alloc(sbase + OFF_TMEM, 128);
-  for (int i = tid; i < 2 * TM; i += 128) {
-    const int row = i & 127, kc = i >> 7;
-    uint4 v = make_uint4(0, 0, 0, 0);
-    if (kc == 0) v.x = pack2(1.0f, 1.0f);
-    *reinterpret_cast<uint4*>(smem + OFF_ONES + a_chunk(row, kc)) = v;
-  }
-  for (int i = tid; i < TM * 12; i += 128) {
-    const int row = i & 127, kc = i >> 7;
-    float v[8];
-    for (int e = 0; e < 8; ++e) v[e] = A[row * 96 + kc * 8 + e];
-    *reinterpret_cast<uint4*>(smem + OFF_A + a_chunk(row, kc)) = pack8(v);
-  }
+  if (warp == 0) tmem_alloc(sbase + off_bar + 16, 512);
+  for (int i = tid; i < image_bytes / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = reinterpret_cast<const uint4*>(image)[i];
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  const uint32_t tmem_base = *reinterpret_cast<uint32_t*>(smem + off_bar + 16);
+  // clear the dumped columns so that untouched accumulators read as zero
+  for (int c = 0; c < ncols; c += 8) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(tmem_base + ((uint32_t)(warp * 32) << 16) + c), "r"(0) : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+  tc_fence_before();
+  __syncthreads();
   if (tid == 0) {
-    mbar_expect_tx(full, WBLK_BYTES);
-    bulk_g2s(sbase + OFF_W, wblk, WBLK_BYTES, full);
-    mbar_wait(full, 0);
     tc_fence_after();
-    for (int ks = 0; ks < 6; ++ks)
-      umma_f16(tmem_base, make_desc(sbase + OFF_A + ks * 2 * A_LBO, A_LBO, A_SBO), make_desc(sbase + OFF_W + ks * 2 * W_LBO, W_LBO, W_SBO),
-               kIdescN96, ks > 0 ? 1u : 0u);
-    umma_f16(tmem_base, make_desc(sbase + OFF_ONES, A_LBO, A_SBO), make_desc(sbase + OFF_W + 12 * W_LBO, W_LBO, W_SBO), kIdescN96, 1u);
+    for (int i = 0; i < n_ops; ++i) {
+      const dp_mma_op o = ops[i];
+      umma_f16(tmem_base + o.tmem_col, make_desc(sbase + o.a_off, o.a_lbo, o.a_sbo), make_desc(sbase + o.b_off, o.b_lbo, o.b_sbo), o.idesc, o.accumulate);
+    }
     umma_commit(done);
   }
   __syncwarp();
   mbar_wait(done, 0);
   tc_fence_after();
   const int row = warp * 32 + (tid & 31);
-  for (int c = 0; c < 96; c += 16) {
+  for (int c = 0; c < ncols; c += 16) {
     float v[16];
     tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + c, v);
-    for (int i = 0; i < 16; ++i) D[row * 96 + c + i] = v[i];
+    for (int i = 0; i < 16; ++i) out[row * ncols + c + i] = v[i];
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 128); }
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
 }
 
 }  // namespace
@@ -878,23 +875,26 @@ int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, l
   return DP_OK;
 }
 
-// D[128][96] = fp16(A[128][96]) * fp16(W[96][96])^T + bias, all device pointers, fp32.  Diagnostic entry point.
-int tc_selftest(const float* A, const float* Wkn /*[K=96][N=96]*/, const float* bias, float* D, cudaStream_t s) {
-  uint8_t* blk = nullptr;
-  DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&blk), WBLK_BYTES));
-  int rc = pack_block(blk, Wkn, H, 0, 0, bias, s);
-  if (rc == DP_OK) {
-    cudaError_t e = cudaFuncSetAttribute(tc_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-    if (e == cudaSuccess) {
-      tc_selftest_kernel<<<1, 128, SMEM_BYTES, s>>>(A, blk, D);
-      count_launch();
-      e = cudaGetLastError();
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) { set_error(std::string("tc_selftest: ") + cudaGetErrorString(e)); rc = DP_ERR_CUDA; }
+// Diagnostic entry point behind dp_selftest_umma (see include/diffpose_b200.h).
+int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* out_dev, int ncols, cudaStream_t s) {
+  if (image_bytes <= 0 || image_bytes % 16 || image_bytes > 200 * 1024 || n_ops <= 0 || n_ops > 256 || ncols <= 0 || ncols > 512 || ncols % 16) {
+    set_error("dp_selftest_umma: image must be a multiple of 16 B (<= 200 KiB), 1..256 ops, ncols a multiple of 16 (<= 512)");
+    return DP_ERR_INVALID;
   }
-  cudaFree(blk);
-  return rc;
+  dp_mma_op* ops_dev = nullptr;
+  DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&ops_dev), n_ops * sizeof(dp_mma_op)));
+  cudaError_t e = cudaMemcpyAsync(ops_dev, ops_host, n_ops * sizeof(dp_mma_op), cudaMemcpyHostToDevice, s);
+  const int smem = (image_bytes + 15) / 16 * 16 + 64;
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e == cudaSuccess) {
+    tc_lab_kernel<<<1, 128, smem, s>>>(static_cast<const uint8_t*>(image_dev), image_bytes, ops_dev, n_ops, out_dev, ncols);
+    count_launch();
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(ops_dev);
+  if (e != cudaSuccess) { set_error(std::string("dp_selftest_umma: ") + cudaGetErrorString(e)); return DP_ERR_CUDA; }
+  return DP_OK;
 }
 
 }  // namespace dp

@@ -119,10 +119,20 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
 int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                double* sums, float* per_pose, void* stream);
 
-/* Diagnostic: one 128x96x96 tensor-core product through the engine's own operand layouts, descriptors, TMA weight
- * staging and TMEM read-back: d[128][96] = fp16(a[128][96]) * fp16(w_kn[96][96]) + bias[96] (fp32 accumulate).
- * All pointers are device fp32; synchronises the stream.  Used by the GPU tests to isolate layout bugs. */
-int dp_selftest_umma(const float* a, const float* w_kn, const float* bias, float* d, void* stream);
+/* Diagnostic "UMMA lab": copies `smem_image` (device pointer, image_bytes % 16 == 0) to shared memory offset 0, issues the
+ * listed tcgen05.mma.kind::f16 instructions in order (descriptor fields in bytes, offsets relative to the image start;
+ * SWIZZLE_NONE canonical layouts; idesc = the 32-bit instruction descriptor), then writes TMEM lanes 0..127, columns
+ * 0..ncols-1 to tmem_out[128][ncols] (device, fp32).  Synchronises the stream.  The GPU tests use it to pin every operand
+ * flavour the tensor-core engine relies on against numpy. */
+typedef struct dp_mma_op {
+  unsigned a_off, a_lbo, a_sbo;   /* A operand: start, leading-dimension byte offset, stride-dimension byte offset */
+  unsigned b_off, b_lbo, b_sbo;   /* B operand */
+  unsigned idesc;                 /* instruction descriptor (formats, majors, N>>3 at bit 17, M>>4 at bit 24)    */
+  unsigned tmem_col;              /* first accumulator column                                                     */
+  unsigned accumulate;            /* 0: D = A*B, 1: D += A*B                                                      */
+} dp_mma_op;
+int dp_selftest_umma(const void* smem_image, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols,
+                     void* stream);
 
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long dp_launch_count(void);
