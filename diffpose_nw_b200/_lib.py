@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffpose_b200.so")
 
-ENGINE_AUTO, ENGINE_FP32, ENGINE_TC = 0, 1, 2
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCG = 0, 1, 2, 3
 
 
 class DpStep(ctypes.Structure):

@@ -249,7 +249,7 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DP_TRY(pack_fp32(h, params, adj_host, s));
-  if (tc_supported(h->d)) DP_TRY(tc_pack(h, s));
+  if (tc_supported(h->d)) { DP_TRY(tc_pack(h, s)); DP_TRY(tc2_pack(h, s)); }
   h->temb_t.clear();
   h->packed = true;
   return DP_OK;
@@ -257,8 +257,8 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
 
 int dp_set_engine(dp_handle h, int engine) {
   DP_REQUIRE(h, "dp_set_engine: NULL handle");
-  DP_REQUIRE(engine == DP_ENGINE_AUTO || engine == DP_ENGINE_FP32 || engine == DP_ENGINE_TC, "dp_set_engine: unknown engine");
-  if (engine == DP_ENGINE_TC && !tc_supported(h->d)) {
+  DP_REQUIRE(engine == DP_ENGINE_AUTO || engine == DP_ENGINE_FP32 || engine == DP_ENGINE_TC || engine == DP_ENGINE_TCG, "dp_set_engine: unknown engine");
+  if ((engine == DP_ENGINE_TC || engine == DP_ENGINE_TCG) && !tc_supported(h->d)) {
     set_error("dp_set_engine: the tensor-core engine needs hid_dim=96, n_head=4, n_pts=17");
     return DP_ERR_UNSUPPORTED;
   }
@@ -268,8 +268,8 @@ int dp_set_engine(dp_handle h, int engine) {
 
 int dp_get_engine(dp_handle h) {
   if (!h) return DP_ERR_INVALID;
-  if (h->engine == DP_ENGINE_FP32) return DP_ENGINE_FP32;
-  return tc_supported(h->d) ? DP_ENGINE_TC : DP_ENGINE_FP32;
+  if (h->engine == DP_ENGINE_FP32 || !tc_supported(h->d)) return DP_ENGINE_FP32;
+  return h->engine == DP_ENGINE_TCG ? DP_ENGINE_TCG : DP_ENGINE_TC;
 }
 
 int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char* mask, float* out, long n, void* stream) {
@@ -330,7 +330,10 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
     dst = h->hyp_scratch;
   }
   int rc;
-  if (dp_get_engine(h) == DP_ENGINE_TC)
+  const int eng = dp_get_engine(h);
+  if (eng == DP_ENGINE_TCG)
+    rc = tc2_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
+  else if (eng == DP_ENGINE_TC)
     rc = tc_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
   else
     rc = simt_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
@@ -368,6 +371,7 @@ const char* dp_version(void) { return "diffpose_b200 0.1 (sm_100a)"; }
 void dp_destroy(dp_handle h) {
   if (!h) return;
   tc_free(h);
+  tc2_free(h);
   if (h->blob) cudaFree(h->blob);
   if (h->dw) cudaFree(h->dw);
   if (h->temb) cudaFree(h->temb);

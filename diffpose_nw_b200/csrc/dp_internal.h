@@ -73,7 +73,8 @@ struct StepsArg {
   dp_step s[kMaxInlineSteps];
 };
 
-struct TcPack;  // defined in dp_tc.cu
+struct TcPack;   // defined in dp_tc.cu
+struct Tc2Pack;  // defined in dp_tc2.cu
 
 }  // namespace dp
 
@@ -100,6 +101,7 @@ struct dp_model {
   size_t hyp_cap = 0;
 
   dp::TcPack* tc = nullptr;       // tensor-core engine state (fp16 packed weights, ...)
+  dp::Tc2Pack* tc2 = nullptr;     // second-generation tensor-core engine state
   long last_launch[6] = {0, 0, 0, 0, 0, 0};
 };
 
@@ -121,6 +123,12 @@ int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, l
               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
               const unsigned char* mask, cudaStream_t s);
 int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* out_dev, int ncols, cudaStream_t s);
+// dp_tc2.cu
+int tc2_pack(dp_model* m, cudaStream_t s);
+void tc2_free(dp_model* m);
+int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
+               const unsigned char* mask, cudaStream_t s);
 // dp_metrics.cu
 int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                    double* sums, float* per_pose, cudaStream_t s);

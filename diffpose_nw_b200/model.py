@@ -166,15 +166,15 @@ class _FusedBase(nn.Module):
         return out
 
     def set_engine(self, engine):
-        """'auto' | 'fp32' | 'tc' -- which kernel family runs the denoiser (see include/diffpose_b200.h)."""
-        self._engine = {"auto": _lib.ENGINE_AUTO, "fp32": _lib.ENGINE_FP32, "tc": _lib.ENGINE_TC}[engine]
+        """'auto' | 'fp32' | 'tc' | 'tcg' -- which kernel family runs the denoiser (see include/diffpose_b200.h)."""
+        self._engine = {"auto": _lib.ENGINE_AUTO, "fp32": _lib.ENGINE_FP32, "tc": _lib.ENGINE_TC, "tcg": _lib.ENGINE_TCG}[engine]
         if self._handle is not None:
             _lib.check(_lib.load().dp_set_engine(self._handle, self._engine), "dp_set_engine")
         return self
 
     def engine(self):
         self._ensure_packed(self._device())
-        return {1: "fp32", 2: "tc"}[_lib.load().dp_get_engine(self._handle)]
+        return {1: "fp32", 2: "tc", 3: "tcg"}[_lib.load().dp_get_engine(self._handle)]
 
     # ---------------------------------------------------------------- device state
     def _device(self):

@@ -38,8 +38,10 @@ enum dp_status {
 enum dp_engine {
   DP_ENGINE_AUTO = 0,  /* tensor-core engine when the configuration allows it, else fp32            */
   DP_ENGINE_FP32 = 1,  /* fp32 FMA persistent kernel: every contraction in fp32 (bit-level reference) */
-  DP_ENGINE_TC = 2     /* tcgen05 persistent kernel: fp16 operands (11-bit significand, same as TF32),
+  DP_ENGINE_TC = 2,    /* tcgen05 persistent kernel: fp16 operands (11-bit significand, same as TF32),
                           fp32 accumulation in TMEM; hid_dim=96, n_head=4, n_pts=17 only               */
+  DP_ENGINE_TCG = 3    /* second-generation tcgen05 kernel: residual stream in TMEM, the 17x17 graph
+                          operators on the tensor cores too, dedicated MMA-issuer warp (same limits)     */
 };
 
 /* One DDIM step.  The scalars are evaluated by the caller with the reference's own fp32 tensor ops

@@ -19,22 +19,27 @@ def dev():
     return torch.device("cuda:0")
 
 
+EMU = {"tc": E.gcndiff_forward_tc, "tcg": E.gcndiff_forward_tcg}
+ENGINE_ID = {"tc": 2, "tcg": 3}
+
+
+@pytest.mark.parametrize("engine", ["tc", "tcg"])
 @pytest.mark.parametrize("tag", ["A", "A1", "B", "C", "D"])
-def test_tc_engine_vs_emulation_and_oracle(golden, tag):
+def test_tc_engine_vs_emulation_and_oracle(golden, tag, engine):
     cfg, adj, model, sd = build_diff(tag, golden)
-    model = model.to(dev()).set_engine("tc")
-    assert model.engine() == "tc"
+    model = model.to(dev()).set_engine(engine)
+    assert model.engine() == engine
     x, mask = t(golden, f"{tag}.x"), mask_for(tag, golden)
     seq, eta = golden[f"{tag}.seq"].tolist(), float(golden[f"{tag}.eta"])
     noise = t(golden, f"{tag}.noise")
     out = D.generalized_steps(x.to(dev()), mask.to(dev()), seq, model, betas(), eta=eta, noise=noise.to(dev()))[0][-1].cpu()
-    assert model.last_launch()[4] == 2
-    emu = O.ddim_sample(x, mask, seq, lambda a, m, tt: E.gcndiff_forward_tc(sd, adj, 5, 4, a, m, tt), betas(), eta=eta, noise=noise)[0][-1]
+    assert model.last_launch()[4] == ENGINE_ID[engine]
+    emu = O.ddim_sample(x, mask, seq, lambda a, m, tt: EMU[engine](sd, adj, 5, 4, a, m, tt), betas(), eta=eta, noise=noise)[0][-1]
     ref = t(golden, f"{tag}.x_final")
     e_emu = (out - emu).abs().max().item()
     e_ref = (out - ref).abs().max().item()
     amp = (emu - ref).abs().max().item()
-    print(f"{tag}: T={len(seq)} |tc-emu|={e_emu:.2e} |tc-ref|={e_ref:.2e} |emu-ref|={amp:.2e}")
+    print(f"{engine} {tag}: T={len(seq)} |tc-emu|={e_emu:.2e} |tc-ref|={e_ref:.2e} |emu-ref|={amp:.2e}")
     # vs the emulation: only accumulation order, reciprocal-vs-division and fp16 double rounding differ; those are
     # amplified by the sampler dynamics exactly like the operand rounding itself (amp), an indexing bug is not
     assert e_emu < max(1e-4, 1.0 * amp), f"{tag}: kernel disagrees with its rounding-point emulation ({e_emu:.3e})"
@@ -43,14 +48,15 @@ def test_tc_engine_vs_emulation_and_oracle(golden, tag):
     assert e_ref < (1e-2 if tag == "D" else 1e-3)
 
 
-def test_tc_default_init_50_steps():
+@pytest.mark.parametrize("engine", ["tc", "tcg"])
+def test_tc_default_init_50_steps(engine):
     """BASELINE configs[3] schedule (T = 50, H = 2, eta = 1) on default-init weights: within 1e-3 of the fp32 oracle."""
     cfg = O.default_config()
     adj = D.adj_mx_from_edges()
     torch.manual_seed(0)
     model = D.FusedGCNdiff(adj, cfg)
     sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    model = model.to(dev()).set_engine("tc")
+    model = model.to(dev()).set_engine(engine)
     B, Hh, seq = 16, 2, list(range(50))
     x = O.synthetic_poses(B, seed=3)
     g = torch.Generator().manual_seed(11)
@@ -66,13 +72,14 @@ def test_tc_default_init_50_steps():
     assert err < 1e-3 and abs(m_ref - m_out) < 0.05
 
 
-def test_tc_matches_fp32_engine_on_many_tiles():
+@pytest.mark.parametrize("engine", ["tc", "tcg"])
+def test_tc_matches_fp32_engine_on_many_tiles(engine):
     """Multi-tile / ragged last tile / persistent loop: 1500 poses on both engines."""
     cfg = O.default_config()
     torch.manual_seed(0)
     model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev())
     x = O.synthetic_poses(1500, seed=12).to(dev())
     a = D.generalized_steps(x, None, [0, 12], model.set_engine("fp32"), betas())[0][-1]
-    b = D.generalized_steps(x, None, [0, 12], model.set_engine("tc"), betas())[0][-1]
+    b = D.generalized_steps(x, None, [0, 12], model.set_engine(engine), betas())[0][-1]
     assert (a - b).abs().max().item() < 1e-3
     assert torch.equal(b, D.generalized_steps(x, None, [0, 12], model, betas())[0][-1])

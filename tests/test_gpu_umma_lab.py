@@ -70,3 +70,33 @@ def test_transposed_pose_aggregation_mn_major_a(pose):
     d = run_lab(img, ops, 32)
     ref = f16(y[17 * pose:17 * pose + 17, :]).T @ f16(lmat).T        # [128 ch][17]
     assert np.abs(d[:96, :17] - ref[:96]).max() < TOL
+
+
+def _put_tall(img, off, g, lbo=4112):
+    """G [17][17] -> rows 128..144 of a tall K-major operand [256 rows x 32], element (r, k) at off + (k//8)*lbo + r*16 + (k%8)*2"""
+    v = img.view(np.float16)
+    for i in range(17):
+        for k in range(17):
+            v[(off + (k // 8) * lbo + (128 + i) * 16 + (k % 8) * 2) // 2] = np.float16(g[i, k])
+
+
+@pytest.mark.parametrize("poses", [[0], [3], [6], list(range(7))])
+def test_tall_window_graph_aggregation(poses):
+    """OUT = sum_p window_p(G) * ACT[17p .. 17p+31]: the K-major A operand is a 128-row window (16-byte granular start)
+    into a zero-padded tall operand, the activations are an MN-major B operand starting at row 17p (dp_tc2.cu)."""
+    rng = np.random.default_rng(4)
+    g = rng.standard_normal((17, 17))
+    act = rng.standard_normal((128, 96))
+    img = np.zeros(96 * 1024, dtype=np.uint8)
+    AO, TO, TL = 0, 40 * 1024, 4112
+    put_chunkcols(img, AO, act)
+    _put_tall(img, TO, g, TL)
+    ops = []
+    for p in poses:
+        for s in range(2):
+            ops.append((TO + (128 - 17 * p) * 16 + s * 2 * TL, TL, 128, AO + (17 * p + 16 * s) * 16, 128, CC, idesc(96, b_mn=True), 0, int(len(ops) > 0)))
+    d = run_lab(img, ops, 96)
+    ref = np.zeros((128, 96))
+    for p in poses:
+        ref[17 * p:17 * p + 17] = f16(g) @ f16(act[17 * p:17 * p + 17])
+    assert np.abs(d - ref).max() < TOL
