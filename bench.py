@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cpn1024", choices=sorted(WORKLOADS))
-    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc", "tcg"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -295,7 +295,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands / f32 accumulate (tcgen05)" if model.engine() == "tc" else "f32",
+            "dtype": "f16 operands / f32 accumulate (tcgen05)" if model.engine() in ("tc", "tcg") else "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "batch_per_gpu": B, "n_hyp": H, "T": T, "eta": eta, "engine": model.engine(),
                        "l2": f"inputs rotate through a {pool_n * batch_bytes / 2**20:.0f} MiB pool (> 126 MiB L2) when steps+warmup >= {pool_n}; "

@@ -34,6 +34,9 @@ SIGNATURES = {
     "dp_sample": (_I, [_P, _P, _I, _P, _L, _I, ctypes.POINTER(DpStep), _I, _P, _P, _I, _P]),
     "dp_metrics": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P]),
     "dp_selftest_umma": (_I, [_P, _I, _P, _I, _P, _I, _P]),
+    "dp_selftest_umma_ts": (_I, [_P, _I, _P, _I, _I, _P, _I, _P, _I, _P]),
+    "dp_selftest_cycles": (_I, [ctypes.POINTER(ctypes.c_longlong)]),
+    "dp_set_trace": (_I, [_P, _P, _I]),
     "dp_launch_count": (_L, []),
     "dp_last_launch_info": (_I, [_P, ctypes.POINTER(_L)]),
     "dp_last_error": (ctypes.c_char_p, []),

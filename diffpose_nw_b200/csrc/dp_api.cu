@@ -354,7 +354,27 @@ int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float*
 int dp_selftest_umma(const void* smem_image, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols,
                      void* stream) {
   DP_REQUIRE(smem_image && ops_host && tmem_out, "dp_selftest_umma: NULL argument");
-  return tc_lab(smem_image, image_bytes, ops_host, n_ops, tmem_out, ncols, static_cast<cudaStream_t>(stream));
+  return tc_lab(smem_image, image_bytes, ops_host, n_ops, tmem_out, ncols, nullptr, 0, 0, static_cast<cudaStream_t>(stream));
+}
+
+int dp_selftest_umma_ts(const void* smem_image, int image_bytes, const void* tmem_image, int tmem_col0, int tmem_ncols,
+                        const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols, void* stream) {
+  DP_REQUIRE(smem_image && tmem_image && ops_host && tmem_out, "dp_selftest_umma_ts: NULL argument");
+  return tc_lab(smem_image, image_bytes, ops_host, n_ops, tmem_out, ncols, tmem_image, tmem_col0, tmem_ncols, static_cast<cudaStream_t>(stream));
+}
+
+int dp_selftest_cycles(long long* out2) {
+  DP_REQUIRE(out2, "dp_selftest_cycles: NULL argument");
+  tc_lab_cycles(out2);
+  return DP_OK;
+}
+
+int dp_set_trace(dp_handle h, long long* dev_buf, int capacity) {
+  DP_REQUIRE(h, "dp_set_trace: NULL handle");
+  DP_REQUIRE(capacity >= 0 && (dev_buf != nullptr || capacity == 0), "dp_set_trace: bad buffer");
+  h->trace = capacity > 0 ? dev_buf : nullptr;
+  h->trace_cap = capacity;
+  return DP_OK;
 }
 
 long dp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }

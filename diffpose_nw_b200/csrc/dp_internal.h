@@ -103,6 +103,8 @@ struct dp_model {
   dp::TcPack* tc = nullptr;       // tensor-core engine state (fp16 packed weights, ...)
   dp::Tc2Pack* tc2 = nullptr;     // second-generation tensor-core engine state
   long last_launch[6] = {0, 0, 0, 0, 0, 0};
+  long long* trace = nullptr;     // caller-owned device buffer for the hand-over timestamps (dp_set_trace)
+  int trace_cap = 0;
 };
 
 namespace dp {
@@ -122,7 +124,9 @@ void tc_free(dp_model* m);
 int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
               const unsigned char* mask, cudaStream_t s);
-int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* out_dev, int ncols, cudaStream_t s);
+int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* out_dev, int ncols,
+           const void* tmem_image_dev, int tmem_col0, int tmem_ncols, cudaStream_t s);
+void tc_lab_cycles(long long* out2);
 // dp_tc2.cu
 int tc2_pack(dp_model* m, cudaStream_t s);
 void tc2_free(dp_model* m);

@@ -48,6 +48,9 @@ constexpr int kThreads = kComputeThreads + 64;
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_X = 0;        // residual stream
 constexpr uint32_t COL_ACC = 96;     // GEMM accumulators (up to 288 columns)
+constexpr uint32_t COL_S0 = 96;      // attention: scores of the even head of a pair [128 x 128]; its probabilities
+constexpr uint32_t COL_S1 = 224;     //   overwrite the first 64 columns as packed fp16 (A operand of P V); odd head
+constexpr uint32_t COL_O = 352;      // attention output [128 x 96] (+8 scratch columns)
 
 // shared memory map (bytes)
 constexpr int al16(int x) { return (x + 15) / 16 * 16; }
@@ -119,6 +122,14 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
       "r"(accum) : "memory");
 }
+// same with the A operand in tensor memory (lane = row, 32-bit column c = elements K = 2c, 2c+1)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
+      "r"(accum) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -174,6 +185,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 // (0 = K-major, 1 = MN-major), N>>3 at 17, M>>4 at 24
 constexpr uint32_t kIdescN96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 constexpr uint32_t kIdescN96BMn = kIdescN96 | (1u << 16);
+constexpr uint32_t kIdescN128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+constexpr uint32_t kIdescN32BMn = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 // byte offset of the 16-byte chunk holding elements (row, 8*kc .. 8*kc+7) inside an fp16 operand block
 __device__ __forceinline__ uint32_t a_chunk(int row, int kc) { return kc * A_LBO + row * 16; }
@@ -208,10 +221,14 @@ struct Tc2Args {
   const float* noise;
   const unsigned char* mask;
   const dp_step* steps_dev;
+  long long* trace;          // optional diagnostic: CTA 0 records clock64() at every hand-over (see dp_set_trace)
+  int trace_cap;
 };
 
 // ------------------------------------------------------------------------------------------------ compute-warp pieces
 struct Ctx {
+  long long* trace;     // non-null on one thread of CTA 0 only
+  int trace_n, trace_cap;
   uint8_t* smem;
   uint32_t tmem_lane;   // tmem base + (lane quarter << 16)
   uint32_t rdy, acc;    // mbarrier addresses
@@ -220,7 +237,11 @@ struct Ctx {
 };
 
 // "my operands are in shared memory / my TMEM reads are done": one arrival per compute warp
+__device__ __forceinline__ void trace_mark(Ctx& c) {
+  if (c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = clock64();
+}
 __device__ __forceinline__ void signal_ready(Ctx& c) {
+  trace_mark(c);
   fence_async_smem();
   tc_fence_before();
   __syncwarp();
@@ -230,6 +251,7 @@ __device__ __forceinline__ void wait_acc(Ctx& c) {
   mbar_wait(c.acc, c.acc_phase);
   c.acc_phase ^= 1;
   tc_fence_after();
+  trace_mark(c);
 }
 
 // 48 fp32 values of (row, channels 48*hh..) -> fp16 operand block `blk`
@@ -285,60 +307,65 @@ __device__ __forceinline__ void epi_group(const Ctx& c, uint32_t col0, int blk, 
   store_half_row(c, blk, v);
 }
 
-// Multi-head attention over the joints of each pose (GraFormer.py:99-113), fp16 q/k/v in operand blocks 0/1/2,
-// output written in place of q.  One thread per (head, pose, query joint).
-__device__ __forceinline__ void attention_tile(uint8_t* smem, int npose) {
-  const float* maskf = reinterpret_cast<const float*>(smem + OFF_MASK);
-  const uint8_t* Q = smem + OFF_A;
-  const uint8_t* K = Q + ABLK_BYTES;
-  const uint8_t* V = K + ABLK_BYTES;
-  const float scale = 1.0f / sqrtf(24.0f);
-  const int per_head = npose * NP;
-  for (int task = threadIdx.x; task < 4 * per_head; task += kComputeThreads) {
-    const int h = task / per_head, rr = task - h * per_head;   // rr = pose*17 + joint = tile row
-    const int p = rr / NP;
-    float q[24];
+// Softmax of one head's scores for this thread's row (GraFormer.py:104-111).  The scores of the whole tile sit in
+// TMEM as S[128 x 128] (row = query, column = key row of the tile); a row only needs the 17 columns of its own pose.
+// The 32 rows of a warp span at most three poses, so the warp loads one window of 48/64 columns and every lane picks
+// its pose's 17 with selects at compile-time offsets.  The probabilities go back to TMEM as fp16 pairs, zero outside the
+// pose (block-diagonal P[128 x 128]), and feed the P V product as its A operand.
+template <int WQ>
+__device__ __forceinline__ void softmax_row(const Ctx& c, uint32_t region, bool has_mask) {
+  constexpr int START = WQ == 0 ? 0 : WQ == 1 ? 16 : WQ == 2 ? 48 : 80;     // first loaded column
+  constexpr int WIN = (WQ == 0 || WQ == 3) ? 48 : 64;                       // loaded columns
+  constexpr int P0 = WQ == 0 ? 0 : WQ == 1 ? 1 : WQ == 2 ? 3 : 5;           // first pose of the warp's rows
+  constexpr int NPOSE = (WQ == 0 || WQ == 3) ? 2 : 3;
+  float v[WIN];
 #pragma unroll
-    for (int cc = 0; cc < 3; ++cc) unpack8(*reinterpret_cast<const uint4*>(Q + a_chunk(rr, 3 * h + cc)), q + 8 * cc);
-    float sc[NP];
-    float mx = -INFINITY;
+  for (int i = 0; i < WIN; i += 16) tmem_ld16_async(region + START + i, v + i);
+  tmem_ld_wait();
+  launder<WIN>(v);
+  const int q = min(c.row / NP, TP - 1) - P0;      // pad rows 119..127 ride along as pose 6
+  const float* maskf = reinterpret_cast<const float*>(c.smem + OFF_MASK);
+  const float scale = 0.20412414523193151f;        // 1 / sqrt(24)
+  float sc[NP];
+  float mx = -INFINITY;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const int rj = p * NP + j;
-      float s = 0.f;
+  for (int j = 0; j < NP; ++j) {
+    float t = q == 0 ? v[NP * P0 - START + j] : v[NP * (P0 + 1) - START + j];
+    if (NPOSE == 3) t = q == 2 ? v[NP * (P0 + 2) - START + j] : t;
+    t *= scale;
+    if (has_mask && maskf[j] == 0.f) t = -1e9f;
+    sc[j] = t;
+    mx = fmaxf(mx, t);
+  }
+  float sum = 0.f;
 #pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        float kv[8];
-        unpack8(*reinterpret_cast<const uint4*>(K + a_chunk(rj, 3 * h + cc)), kv);
+  for (int j = 0; j < NP; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.0f / sum;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) s = fmaf(q[8 * cc + e], kv[e], s);
-      }
-      s = s * scale;
-      if (maskf[j] == 0.f) s = -1e9f;
-      sc[j] = s;
-      mx = fmaxf(mx, s);
-    }
-    float sum = 0.f;
+  for (int j = 0; j < NP; ++j) sc[j] *= inv;
+  // K position x of P (x = key row of the tile): pose x/17 (static), joint x%17
+  auto pick = [&](int x) -> float {
+    if (x < NP * P0 || x >= NP * (P0 + NPOSE) || x >= TR) return 0.f;
+    return (q == x / NP - P0) ? sc[x % NP] : 0.f;
+  };
 #pragma unroll
-    for (int j = 0; j < NP; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
-    const float inv = 1.0f / sum;
-    float o[24];
+  for (int piece = 0; piece < 4; ++piece) {
+    uint32_t pk[16];
 #pragma unroll
-    for (int e = 0; e < 24; ++e) o[e] = 0.f;
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const int rj = p * NP + j;
-      const float pj = sc[j] * inv;
-#pragma unroll
-      for (int cc = 0; cc < 3; ++cc) {
-        float vv[8];
-        unpack8(*reinterpret_cast<const uint4*>(V + a_chunk(rj, 3 * h + cc)), vv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) o[8 * cc + e] = fmaf(pj, vv[e], o[8 * cc + e]);
-      }
-    }
-#pragma unroll
-    for (int cc = 0; cc < 3; ++cc) *reinterpret_cast<uint4*>(smem + OFF_A + a_chunk(rr, 3 * h + cc)) = pack8(o + 8 * cc);
+    for (int i = 0; i < 16; ++i) pk[i] = pack2(pick(32 * piece + 2 * i), pick(32 * piece + 2 * i + 1));
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(region + 16 * piece),
+        "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
+        "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]) : "memory");
+  }
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void softmax_dispatch(const Ctx& c, int wq, uint32_t region, bool has_mask) {
+  switch (wq) {
+    case 0: softmax_row<0>(c, region, has_mask); break;
+    case 1: softmax_row<1>(c, region, has_mask); break;
+    case 2: softmax_row<2>(c, region, has_mask); break;
+    default: softmax_row<3>(c, region, has_mask); break;
   }
 }
 
@@ -419,7 +446,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, rdy_phase = 0;
       const uint32_t ones = sbase + OFF_ONES;
-      auto wait_rdy = [&]() { mbar_wait(rdy, rdy_phase); rdy_phase ^= 1; tc_fence_after(); };
+      long long* itrace = (blockIdx.x == 0 && a.trace != nullptr) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
+      int itrace_n = 0;
+      auto imark = [&]() { if (itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
+      auto wait_rdy = [&]() { imark(); mbar_wait(rdy, rdy_phase); rdy_phase ^= 1; tc_fence_after(); imark(); };
       auto w_acquire = [&]() -> uint32_t { mbar_wait(full0 + 8 * stage, phase); tc_fence_after(); return sbase + OFF_W + stage * WBLK_BYTES; };
       auto w_release = [&]() { umma_commit(empty0 + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } };
       // D[:, dcol..dcol+96) (+)= block a_blk [128 x 96] * W^T
@@ -443,6 +473,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             umma_f16(tmem_base + dcol, make_desc(ta + (128 - NP * p) * 16 + s * 2 * T_LBO, T_LBO, 128),
                      make_desc(ba + (NP * p + 16 * s) * 16, 128, A_LBO), kIdescN96BMn, (accumulate || p > 0 || s > 0) ? 1u : 0u);
       };
+      // S_h[:, 0..128) = Q_h K_h^T; Q = block 0, K = block 1, chunk columns 3h..3h+2 (the 4th one of the second K step is
+      // the zero chunk column behind the ones slab for Q, whatever follows for K)
+      auto scores_head = [&](int h, uint32_t dcol) {
+        const uint32_t qa = sbase + OFF_A + 3 * h * A_LBO, ka = sbase + OFF_A + ABLK_BYTES + 3 * h * A_LBO;
+        umma_f16(tmem_base + dcol, make_desc(qa, A_LBO, A_SBO), make_desc(ka, A_LBO, A_SBO), kIdescN128, 0u);
+        umma_f16(tmem_base + dcol, make_desc(qa + 2 * A_LBO, (sbase + OFF_ONES + A_LBO) - (qa + 2 * A_LBO), A_SBO),
+                 make_desc(ka + 2 * A_LBO, A_LBO, A_SBO), kIdescN128, 1u);
+      };
+      // O[:, 24h..24h+32) = P_h V[:, 24h..24h+32): P_h in TMEM at pcol (64 packed columns), V = block 2 (MN-major)
+      auto pv_head = [&](int h, uint32_t pcol) {
+        const uint32_t va = sbase + OFF_A + 2 * ABLK_BYTES + 3 * h * A_LBO;
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks)
+          umma_f16_ts(tmem_base + COL_O + 24 * h, tmem_base + pcol + 8 * ks, make_desc(va + ks * 256, 128, A_LBO), kIdescN32BMn, ks > 0 ? 1u : 0u);
+      };
       for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int step = 0; step < a.n_steps; ++step)
           for (int l = 0; l < L; ++l) {
@@ -451,6 +496,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             wait_rdy();
             for (int part = 0; part < 3; ++part) { wa = w_acquire(); gemm(wa, 2, COL_ACC + 96 * part, false); bias(wa, COL_ACC + 96 * part); w_release(); }
             umma_commit(accb);
+            // 1b. attention, two heads at a time: S = Q_h K_h^T (d_k = 24 = K step of 16 + 8 real | 8 zero columns),
+            //     softmax on the compute warps (P back into TMEM), O_h = P V_h with V as an MN-major operand
+            for (int pair = 0; pair < 3; ++pair) {
+              wait_rdy();
+              if (pair > 0)
+                for (int e = 0; e < 2; ++e) pv_head(2 * (pair - 1) + e, e ? COL_S1 : COL_S0);
+              if (pair < 2)
+                for (int e = 0; e < 2; ++e) scores_head(2 * pair + e, e ? COL_S1 : COL_S0);
+              umma_commit(accb);
+            }
             // 2. x += attn Wo + bo                              A = block 0
             wait_rdy();
             wa = w_acquire(); gemm(wa, 0, COL_X, true); bias(wa, COL_X); w_release();
@@ -506,9 +561,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     c.hh = warp >> 2;
     c.tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
     c.rdy = rdy; c.acc = accb; c.acc_phase = 0;
+    c.trace = (blockIdx.x == 0 && tid == 0) ? a.trace : nullptr;
+    c.trace_n = 0; c.trace_cap = a.trace_cap / 2;
     const int row = c.row, hh = c.hh;
     float* scratch = reinterpret_cast<float*>(smem + OFF_A);   // [128][16] fp32, aliases the head of operand block 0
     const float* temb_s = reinterpret_cast<const float*>(smem + OFF_TE);
+    const bool has_mask = a.mask != nullptr;
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
@@ -590,9 +648,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
 #pragma unroll
             for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + a_chunk(row, kc0 + q)) = pack8(v + 8 * q);
           }
-          tc_fence_before();
-          bar_compute();
-          attention_tile(smem, TP);
+          signal_ready(c);                                         // -> scores of heads 0, 1
+          wait_acc(c);
+          softmax_dispatch(c, warp & 3, c.tmem_lane + (hh ? COL_S1 : COL_S0), has_mask);
+          signal_ready(c);                                         // -> P V of heads 0, 1; scores of heads 2, 3
+          wait_acc(c);
+          softmax_dispatch(c, warp & 3, c.tmem_lane + (hh ? COL_S1 : COL_S0), has_mask);
+          signal_ready(c);                                         // -> P V of heads 2, 3
+          wait_acc(c);
+          epi_group<0>(c, COL_O, 0, nullptr);
           signal_ready(c);                                         // -> 2
           wait_acc(c);
           // ======== x = x + GraphNet(LN1(x))
@@ -784,6 +848,7 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
   a.w = m->dw; a.wpack = m->tc2->blocks; a.n_layer = m->d.n_layer; a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
   a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_steps = n_steps; a.temb = m->temb; a.noise = noise; a.mask = mask;
   a.steps_dev = steps_dev;
+  a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
   tc2_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);

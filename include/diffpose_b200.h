@@ -131,10 +131,24 @@ typedef struct dp_mma_op {
   unsigned b_off, b_lbo, b_sbo;   /* B operand */
   unsigned idesc;                 /* instruction descriptor (formats, majors, N>>3 at bit 17, M>>4 at bit 24)    */
   unsigned tmem_col;              /* first accumulator column                                                     */
-  unsigned accumulate;            /* 0: D = A*B, 1: D += A*B                                                      */
+  unsigned accumulate;            /* bit 0: 0 D = A*B, 1 D += A*B; bit 1 (dp_selftest_umma_ts): A is in TMEM at column a_off */
 } dp_mma_op;
 int dp_selftest_umma(const void* smem_image, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols,
                      void* stream);
+/* Same, after preloading tensor memory: tmem_image is a device array [128 lanes][tmem_ncols] of 32-bit words written to
+ * columns tmem_col0.. (tmem_ncols % 8 == 0); ops with accumulate bit 1 read their A operand from TMEM (two fp16 per word). */
+int dp_selftest_umma_ts(const void* smem_image, int image_bytes, const void* tmem_image, int tmem_col0, int tmem_ncols,
+                        const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols, void* stream);
+
+/* SM cycles of the last dp_selftest_umma[_ts] launch: out2[0] = to issue all MMAs and the commit (one thread),
+ * out2[1] = from the first issue until the committed mbarrier was observed (host array of 2). */
+int dp_selftest_cycles(long long* out2);
+
+/* Diagnostic: while dev_buf is set (device pointer, `capacity` 64-bit slots; NULL/0 switches it off), thread 0 of CTA 0 of
+ * the DP_ENGINE_TCG kernel stores clock64() at every hand-over between the compute warps and the MMA issuer ("operands
+ * ready" just before it is signalled, "accumulator ready" just after it is observed), in program order.  Used by
+ * tools/phase_trace.py to attribute the per-layer time to the individual epilogues and MMA groups. */
+int dp_set_trace(dp_handle h, long long* dev_buf, int capacity);
 
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long dp_launch_count(void);

@@ -43,5 +43,17 @@ def run_lab(img, ops, ncols):
     return out.cpu().numpy().astype(np.float64)
 
 
+def run_lab_ts(img, timg, tcol0, ops, ncols):
+    """timg: [128][ncols_t] float16 pairs packed as uint32 (lane = row) preloaded at TMEM column tcol0."""
+    dev = torch.device("cuda:0")
+    image = torch.from_numpy(img.copy()).to(dev)
+    t = torch.from_numpy(np.ascontiguousarray(timg).view(np.int32).copy()).to(dev)
+    arr = (_lib.DpMmaOp * len(ops))(*[_lib.DpMmaOp(*o) for o in ops])
+    out = torch.zeros(128, ncols, device=dev)
+    _lib.check(_lib.load().dp_selftest_umma_ts(image.data_ptr(), image.numel(), t.data_ptr(), tcol0, t.shape[1], arr, len(ops),
+                                               out.data_ptr(), ncols, None), "dp_selftest_umma_ts")
+    return out.cpu().numpy().astype(np.float64)
+
+
 def f16(x):
     return x.astype(np.float16).astype(np.float64)

@@ -19,7 +19,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-EMU = {"tc": E.gcndiff_forward_tc, "tcg": E.gcndiff_forward_tcg}
+EMU = {"tc": E.gcndiff_forward_tc, "tcg": lambda *a: E.gcndiff_forward_tcg(*a, p16=True)}
 ENGINE_ID = {"tc": 2, "tcg": 3}
 
 

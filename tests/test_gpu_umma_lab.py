@@ -100,3 +100,20 @@ def test_tall_window_graph_aggregation(poses):
     for p in poses:
         ref[17 * p:17 * p + 17] = f16(g) @ f16(act[17 * p:17 * p + 17])
     assert np.abs(d - ref).max() < TOL
+
+
+@pytest.mark.parametrize("h", [0, 3])
+def test_pv_with_p_in_tmem(h):
+    """O_h = P V_h with P (fp16, two per 32-bit column, lane = row) read from tensor memory as the A operand and V in
+    the activation layout consumed as an MN-major B operand."""
+    from _umma import run_lab_ts
+    rng = np.random.default_rng(5)
+    p, v = rng.random((128, 128)), rng.standard_normal((128, 104))
+    img = np.zeros(64 * 1024, dtype=np.uint8)
+    put_chunkcols(img, 0, v)
+    timg = p.astype(np.float16).view(np.uint32).reshape(128, 64)     # little endian: low half = even k
+    TC0 = 256
+    ops = [(TC0 + 8 * s, 0, 0, 3 * h * CC + s * 256, 128, CC, idesc(32, b_mn=True), 0, 2 | int(s > 0)) for s in range(8)]
+    d = run_lab_ts(img, timg, TC0, ops, 32)
+    ref = f16(p) @ f16(v[:, 24 * h:24 * h + 32])
+    assert np.abs(d - ref).max() < TOL
