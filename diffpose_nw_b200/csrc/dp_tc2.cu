@@ -1,18 +1,26 @@
 // Tensor-core engine, second generation ("tcg"): persistent sm_100a kernel, one 128-row tile (7 poses x 17 joints) per
-// CTA, all DDIM steps and layers executed without leaving the SM.  Compared with dp_tc.cu:
+// CTA, all DDIM steps and layers executed without leaving the SM.  Every contraction of the denoiser runs on tcgen05:
 //
+//   * dense projections (QKV, out-proj, GraphNet fc1/fc2, Chebyshev convolutions) as M=128, N=96, K=16 fp16 MMAs with
+//     fp32 accumulators in TMEM; biases ride along as one extra K step against a constant-one slab;
 //   * the residual stream X lives in TMEM (96 fp32 columns).  Residual additions are free: the out-projection, the
 //     second GraphNet aggregation and the b2 bias accumulate straight into those columns (D += A*B);
-//   * the 17x17 graph operators (Chebyshev T1/T2, learnable-adjacency L^) run on the tensor cores as well.  A graph
-//     matrix G is stored once as a "tall" K-major operand [256 rows x 32] whose rows 128..144 hold G and every other
-//     row is zero; the window starting at row 128-17p is the 128x32 matrix that applies G to pose p and nothing to the
-//     other poses.  The activations are consumed in place as an MN-major B operand starting at row 17p, so
-//     OUT[128 x 96] = sum_p window_p(G) * ACT[17p .. 17p+31][96] needs 14 MMAs and no data movement;
-//   * a dedicated warp issues every tcgen05.mma; the 8 compute warps only run epilogues (TMEM -> registers -> fp16
-//     operand in shared memory), LayerNorm, attention and the DDIM update, and hand over through two mbarriers
-//     ("operands ready" 8 arrivals, "accumulator ready" by tcgen05.commit);
-//   * weights stream L2 -> shared memory through a 4-stage ring of 21.5 KB pre-packed blocks (cp.async.bulk + mbarrier
-//     complete_tx) issued by a producer warp.
+//   * the 17x17 graph operators (Chebyshev T1/T2, learnable-adjacency L^).  A graph matrix G is stored once as a "tall"
+//     K-major operand [256 rows x 32] whose rows 128..144 hold G and every other row is zero; the window starting at row
+//     128-17p is the 128x32 matrix that applies G to pose p and nothing to the other poses.  The activations are
+//     consumed in place as an MN-major B operand starting at row 17p, so OUT[128 x 96] = sum_p window_p(G) *
+//     ACT[17p .. 17p+31][96] needs 14 MMAs and no data movement;
+//   * attention: S_h = Q_h K_h^T for the whole tile (N = 128 key rows), softmax on the compute warps straight out of
+//     TMEM (each row keeps the 17 columns of its own pose), probabilities written back to TMEM as packed fp16 and used
+//     as the A operand of O_h = P_h V_h (V consumed in place as an MN-major operand);
+//   * the input (K = 15) and output (N = 15) Chebyshev convolutions with hi/lo fp16 splits of both operands (three
+//     MMAs per product), i.e. at fp32-level accuracy.
+//
+// Warp roles: 8 compute warps (epilogues TMEM -> registers -> fp16 operand in shared memory, LayerNorm, softmax, DDIM
+// update), one producer warp (weights and per-layer parameters L2 -> shared memory with cp.async.bulk + mbarrier
+// complete_tx, 4-stage ring of 21.5 KB blocks), one issuer warp (every tcgen05.mma, following a static per-layer
+// program).  Compute warps and issuer hand over through two mbarriers ("operands ready": 8 arrivals, "accumulator
+// ready": tcgen05.commit).
 //
 // Reference semantics: see the list at the top of dp_simt.cu (same functions, same file:line).
 #include <cuda_fp16.h>
@@ -41,6 +49,11 @@ constexpr int T_ROWS = 256;                         // tall graph operand: rows 
 constexpr int T_LBO = T_ROWS * 16 + 16;             // 4112
 constexpr int TALL_BYTES = 4 * T_LBO;               // 16448 (K padded to 32)
 constexpr int BLOCKS_PER_LAYER = 14;
+constexpr int OUT_LBO = 256;                        // output-convolution block: N = 16 rows, K-adjacent core matrices 256 B apart
+constexpr int LP_LN_BYTES = 4 * H * 4;              // per-layer parameters: ln0_a, ln0_b, ln1_a, ln1_b (fp32)
+constexpr int LP_LHAT_BYTES = 4 * NP * 16;          //   + L^ as fp16 [4 chunk columns][17 rows][8]
+constexpr int LP_BYTES = LP_LN_BYTES + LP_LHAT_BYTES;   // 2624, copied from the packed parameter array
+constexpr int PAR_BYTES = LP_BYTES + H * 4;         // + temb of this (step, layer): 3008 per stage
 constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
 constexpr int kComputeThreads = 256;
 constexpr int kProducerWarp = 8, kIssuerWarp = 9;
@@ -55,22 +68,21 @@ constexpr uint32_t COL_O = 352;      // attention output [128 x 96] (+8 scratch 
 // shared memory map (bytes)
 constexpr int al16(int x) { return (x + 15) / 16 * 16; }
 constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][16] aliases block 0
-constexpr int OFF_ONES = OFF_A + 3 * ABLK_BYTES;           // constant-one K slab (bias rides in the MMA)
+constexpr int OFF_ONES = OFF_A + 3 * ABLK_BYTES;           // constant-one K slab (bias rides in the MMA) + a zero chunk column
 constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
 constexpr int OFF_W = (OFF_TALL + 3 * TALL_BYTES + 127) / 128 * 128;
 constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][8] fp32
-constexpr int OFF_EP = OFF_XT + TM * 8 * 4;                // eps [128][8] fp32
-constexpr int OFF_NBI = OFF_EP + TM * 8 * 4;               // neighbour index  [17][9] int
+constexpr int OFF_PAR = OFF_XT + TM * 8 * 4;               // per-layer parameters, 2 stages
+constexpr int OFF_NBI = OFF_PAR + 2 * PAR_BYTES;           // neighbour index  [17][9] int
 constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
 constexpr int OFF_STAT = al16(OFF_NBC + NP * NNB * 8);     // LayerNorm partial statistics [2][128] float2
-constexpr int OFF_TE = OFF_STAT + 2 * TM * 8;              // temb of the current (step, layer) [96]
-constexpr int OFF_MASK = OFF_TE + H * 4;                   // key mask [32]
-constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], rdy, acc
+constexpr int OFF_MASK = OFF_STAT + 2 * TM * 8;            // key mask [32]
+constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], rdy, acc
 constexpr int OFF_TMEM = OFF_BAR + 128;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_TALL % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
-              OFF_STAT % 16 == 0, "alignment");
+              OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -106,6 +118,11 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
@@ -114,24 +131,40 @@ __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], kind::f16, single CTA
-__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+
+// Shared-memory matrix descriptor, canonical SWIZZLE_NONE layout (cute::UMMA::SmemDescriptor):
+// bits [0,14) start>>4, [16,30) leading-dimension byte offset>>4, [32,46) stride-dimension byte offset>>4, [46,48) version=1.
+// The issuer keeps descriptors as (lo, hi) words: moving the start address is an add on the low word.
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo) { return ((saddr & 0x3FFFFu) >> 4) | ((lbo >> 4) << 16); }
+constexpr uint32_t desc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (0), A major bit 15, B major bit 16
+// (0 = K-major, 1 = MN-major), N>>3 at 17, M>>4 at 24
+constexpr uint32_t idesc_f16(uint32_t n, bool b_mn) { return (1u << 4) | ((b_mn ? 1u : 0u) << 16) | ((n >> 3) << 17) | ((128u >> 4) << 24); }
+
+// D[tmem] (+)= A[smem] * B[smem], kind::f16, single CTA; issued by the lane whose `leader` is set
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+                                        uint32_t accum, uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc),
-      "r"(accum) : "memory");
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\tsetp.ne.b32 q, %7, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi),
+      "r"(idesc), "r"(accum), "r"(leader) : "memory");
 }
 // same with the A operand in tensor memory (lane = row, 32-bit column c = elements K = 2c, 2c+1)
-__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accum,
+                                        uint32_t leader) {
   asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc),
-      "r"(accum) : "memory");
+      "{\n\t.reg .pred p, q;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\tsetp.ne.b32 q, %6, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(tmem_d), "r"(tmem_a), "r"(b_lo), "r"(b_hi), "r"(idesc),
+      "r"(accum), "r"(leader) : "memory");
 }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint32_t leader) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar), "r"(leader) : "memory");
 }
 
 // TMEM -> registers, 16 consecutive fp32 columns of this thread's lane; completion is NOT awaited here
@@ -176,17 +209,11 @@ __device__ __forceinline__ void tmem_st48(uint32_t taddr, const float* v) {
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
-// Shared-memory matrix descriptor, canonical SWIZZLE_NONE layout (cute::UMMA::SmemDescriptor):
-// bits [0,14) start>>4, [16,30) leading-dimension byte offset>>4, [32,46) stride-dimension byte offset>>4, [46,48) version=1
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
-// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (0), A major bit 15, B major bit 16
-// (0 = K-major, 1 = MN-major), N>>3 at 17, M>>4 at 24
-constexpr uint32_t kIdescN96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t kIdescN96BMn = kIdescN96 | (1u << 16);
-constexpr uint32_t kIdescN128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
-constexpr uint32_t kIdescN32BMn = (1u << 4) | (1u << 16) | ((32u >> 3) << 17) | ((128u >> 4) << 24);
 
 // byte offset of the 16-byte chunk holding elements (row, 8*kc .. 8*kc+7) inside an fp16 operand block
 __device__ __forceinline__ uint32_t a_chunk(int row, int kc) { return kc * A_LBO + row * 16; }
@@ -198,19 +225,27 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 __device__ __forceinline__ uint4 pack8(const float* v) {
   return make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
 }
-__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
-  const __half2* h = reinterpret_cast<const __half2*>(&u);
+// v = hi + lo with both halves fp16: hi = round(v), lo = round(v - hi)
+__device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
+  float r[8];
+  uint32_t h[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 f = __half22float2(h[i]);
-    v[2 * i] = f.x;
-    v[2 * i + 1] = f.y;
+    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(hh);
+    r[2 * i] = v[2 * i] - f.x;
+    r[2 * i + 1] = v[2 * i + 1] - f.y;
+    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
   }
+  hi = make_uint4(h[0], h[1], h[2], h[3]);
+  lo = pack8(r);
 }
 
 struct Tc2Args {
-  const Weights* w;          // fp32 blob (LayerNorm, L^, in/out convolutions, T1/T2)
+  const Weights* w;          // fp32 blob (T1/T2 for the gathers, output bias)
   const uint8_t* wpack;      // fp16 weight blocks [n_layer][14][21504 B]
+  const uint8_t* ioblocks;   // [2][21504 B]: input-convolution block, output-convolution block
+  const uint8_t* lparams;    // [n_layer][LP_BYTES]
   int n_layer;
   const float* x_in;
   int x_is_repeated;
@@ -236,10 +271,10 @@ struct Ctx {
   int row, hh, lane;
 };
 
-// "my operands are in shared memory / my TMEM reads are done": one arrival per compute warp
 __device__ __forceinline__ void trace_mark(Ctx& c) {
   if (c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = clock64();
 }
+// "my operands are in shared memory / my TMEM accesses are done": one arrival per compute warp
 __device__ __forceinline__ void signal_ready(Ctx& c) {
   trace_mark(c);
   fence_async_smem();
@@ -263,34 +298,38 @@ __device__ __forceinline__ void store_half_row(const Ctx& c, int blk, const floa
 
 // LayerNorm (GraFormer.py:67-70: unbiased std, eps added to std) of the residual row held by threads (row, 0) and
 // (row, 1), 48 channels each; the halves exchange (mean, M2) through shared memory and merge them exactly.
-__device__ __forceinline__ void layer_norm_rows(const Ctx& c, float* v, const float* __restrict__ ga, const float* __restrict__ gb) {
-  float s = 0.f;
+// ga/gb: shared-memory copies of a_2 / b_2.
+__device__ __forceinline__ void layer_norm_rows(const Ctx& c, float* v, const float* ga, const float* gb) {
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 48; ++i) s += v[i];
-  const float m = s * (1.0f / 48.0f);
-  float q2 = 0.f;
+  for (int i = 0; i < 48; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
+  const float m = ((s0 + s1) + (s2 + s3)) * (1.0f / 48.0f);
+  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 48; ++i) { const float d = v[i] - m; q2 = fmaf(d, d, q2); }
+  for (int i = 0; i < 48; i += 4) {
+    const float d0 = v[i] - m, d1 = v[i + 1] - m, d2 = v[i + 2] - m, d3 = v[i + 3] - m;
+    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+  }
+  const float qq = (q0 + q1) + (q2 + q3);
   float2* stat = reinterpret_cast<float2*>(c.smem + OFF_STAT);
-  stat[c.hh * TM + c.row] = make_float2(m, q2);
+  stat[c.hh * TM + c.row] = make_float2(m, qq);
   bar_compute();
   const float2 o = stat[(c.hh ^ 1) * TM + c.row];
   const float mean = 0.5f * (m + o.x);
   const float dm = m - o.x;
-  const float m2 = q2 + o.y + dm * dm * 24.0f;
+  const float m2 = qq + o.y + dm * dm * 24.0f;
   const float inv = 1.0f / (sqrtf(m2 * (1.0f / (float)(H - 1))) + 1e-6f);
 #pragma unroll
   for (int q = 0; q < 12; ++q) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(ga + c.hh * 48) + q), b = __ldg(reinterpret_cast<const float4*>(gb + c.hh * 48) + q);
+    const float4 a = *reinterpret_cast<const float4*>(ga + c.hh * 48 + 4 * q), b = *reinterpret_cast<const float4*>(gb + c.hh * 48 + 4 * q);
     v[4 * q] = fmaf(a.x * inv, v[4 * q] - mean, b.x); v[4 * q + 1] = fmaf(a.y * inv, v[4 * q + 1] - mean, b.y);
     v[4 * q + 2] = fmaf(a.z * inv, v[4 * q + 2] - mean, b.z); v[4 * q + 3] = fmaf(a.w * inv, v[4 * q + 3] - mean, b.w);
   }
 }
 
-// accumulator columns [col0 + 48*hh', ...) -> fp16 operand block.  NB96 = number of 96-column groups; group g goes to
-// block blk[g].  KIND: 0 plain, 1 relu, 2 relu + temb (smem vector)
+// accumulator columns [col0 + 48*hh, +48) -> fp16 operand block.  KIND: 0 plain, 1 relu, 2 relu + temb (smem vector)
 template <int KIND>
-__device__ __forceinline__ void epi_group(const Ctx& c, uint32_t col0, int blk, const float* __restrict__ temb) {
+__device__ __forceinline__ void epi_group(const Ctx& c, uint32_t col0, int blk, const float* temb) {
   float v[48];
   tmem_ld48(c.tmem_lane + col0 + c.hh * 48, v);
   if (KIND >= 1) {
@@ -325,22 +364,25 @@ __device__ __forceinline__ void softmax_row(const Ctx& c, uint32_t region, bool 
   launder<WIN>(v);
   const int q = min(c.row / NP, TP - 1) - P0;      // pad rows 119..127 ride along as pose 6
   const float* maskf = reinterpret_cast<const float*>(c.smem + OFF_MASK);
-  const float scale = 0.20412414523193151f;        // 1 / sqrt(24)
+  const float k2 = 0.20412414523193151f * 1.4426950408889634f;   // log2(e) / sqrt(24): softmax(s / sqrt(d_k)) in base 2
   float sc[NP];
   float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     float t = q == 0 ? v[NP * P0 - START + j] : v[NP * (P0 + 1) - START + j];
     if (NPOSE == 3) t = q == 2 ? v[NP * (P0 + 2) - START + j] : t;
-    t *= scale;
-    if (has_mask && maskf[j] == 0.f) t = -1e9f;
+    if (has_mask) t = maskf[j] == 0.f ? -1e9f * 4.898979485566356f : t;     // masked_fill(-1e9) acts after the 1/sqrt(d_k) scaling
     sc[j] = t;
     mx = fmaxf(mx, t);
   }
-  float sum = 0.f;
+  const float mk = mx * k2;
+  float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-  for (int j = 0; j < NP; ++j) { sc[j] = __expf(sc[j] - mx); sum += sc[j]; }
-  const float inv = 1.0f / sum;
+  for (int j = 0; j < NP; ++j) {
+    sc[j] = ex2(fmaf(sc[j], k2, -mk));
+    if (j & 1) s1 += sc[j]; else s0 += sc[j];
+  }
+  const float inv = 1.0f / (s0 + s1);
 #pragma unroll
   for (int j = 0; j < NP; ++j) sc[j] *= inv;
   // K position x of P (x = key row of the tile): pose x/17 (static), joint x%17
@@ -380,18 +422,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
   float* xt = reinterpret_cast<float*>(smem + OFF_XT);
-  float* ep = reinterpret_cast<float*>(smem + OFF_EP);
   float* maskf = reinterpret_cast<float*>(smem + OFF_MASK);
   int* nbi = reinterpret_cast<int*>(smem + OFF_NBI);
   float2* nbc = reinterpret_cast<float2*>(smem + OFF_NBC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   const Weights& w = *a.w;
 
-  const uint32_t full0 = sbase + OFF_BAR, empty0 = sbase + OFF_BAR + 32, rdy = sbase + OFF_BAR + 64, accb = sbase + OFF_BAR + 72;
+  const uint32_t full0 = sbase + OFF_BAR, empty0 = sbase + OFF_BAR + 32, pfull0 = sbase + OFF_BAR + 64, pempty0 = sbase + OFF_BAR + 80,
+                 rdy = sbase + OFF_BAR + 96, accb = sbase + OFF_BAR + 104;
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(pfull0 + 8 * s, 1); mbar_init(pempty0 + 8 * s, kComputeThreads / 32); }
     mbar_init(rdy, kComputeThreads / 32);
     mbar_init(accb, 1);
     fence_mbar_init();
@@ -428,129 +471,177 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   const int L = a.n_layer;
 
   if (warp == kProducerWarp) {
-    // ---------------------------------------------------------------- weight producer (TMA bulk copies)
+    // ---------------------------------------------------------------- producer (TMA bulk copies): per step the input-convolution
+    // block, per layer its parameters (double buffered) + 14 weight blocks, then the output-convolution block
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
+      uint32_t stage = 0, phase = 0, ps = 0, pphase = 0;
+      auto put_block = [&](const uint8_t* src) {
+        mbar_wait_sleep(empty0 + 8 * stage, phase ^ 1);
+        mbar_expect_tx(full0 + 8 * stage, WBLK_BYTES);
+        bulk_g2s(sbase + OFF_W + stage * WBLK_BYTES, src, WBLK_BYTES, full0 + 8 * stage);
+        if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+      };
       for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int step = 0; step < a.n_steps; ++step)
-          for (int blk = 0; blk < L * BLOCKS_PER_LAYER; ++blk) {
-            mbar_wait_sleep(empty0 + 8 * stage, phase ^ 1);
-            mbar_expect_tx(full0 + 8 * stage, WBLK_BYTES);
-            bulk_g2s(sbase + OFF_W + stage * WBLK_BYTES, a.wpack + (size_t)blk * WBLK_BYTES, WBLK_BYTES, full0 + 8 * stage);
-            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+        for (int step = 0; step < a.n_steps; ++step) {
+          put_block(a.ioblocks);
+          for (int l = 0; l < L; ++l) {
+            mbar_wait_sleep(pempty0 + 8 * ps, pphase ^ 1);
+            mbar_expect_tx(pfull0 + 8 * ps, PAR_BYTES);
+            bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES, a.lparams + (size_t)l * LP_BYTES, LP_BYTES, pfull0 + 8 * ps);
+            bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES + LP_BYTES, a.temb + ((size_t)step * L + l) * H, H * 4, pfull0 + 8 * ps);
+            if (++ps == 2) { ps = 0; pphase ^= 1; }
+            for (int blk = 0; blk < BLOCKS_PER_LAYER; ++blk) put_block(a.wpack + ((size_t)l * BLOCKS_PER_LAYER + blk) * WBLK_BYTES);
           }
+          put_block(a.ioblocks + WBLK_BYTES);
+        }
     }
     __syncwarp();
   } else if (warp == kIssuerWarp) {
-    // ---------------------------------------------------------------- MMA issuer: one thread, a static program per layer
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0, rdy_phase = 0;
-      const uint32_t ones = sbase + OFF_ONES;
-      long long* itrace = (blockIdx.x == 0 && a.trace != nullptr) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
-      int itrace_n = 0;
-      auto imark = [&]() { if (itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
-      auto wait_rdy = [&]() { imark(); mbar_wait(rdy, rdy_phase); rdy_phase ^= 1; tc_fence_after(); imark(); };
-      auto w_acquire = [&]() -> uint32_t { mbar_wait(full0 + 8 * stage, phase); tc_fence_after(); return sbase + OFF_W + stage * WBLK_BYTES; };
-      auto w_release = [&]() { umma_commit(empty0 + 8 * stage); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } };
-      // D[:, dcol..dcol+96) (+)= block a_blk [128 x 96] * W^T
-      auto gemm = [&](uint32_t wa, int a_blk, uint32_t dcol, bool accumulate) {
-        const uint32_t aa = sbase + OFF_A + a_blk * ABLK_BYTES;
+    // ---------------------------------------------------------------- MMA issuer: the whole warp runs the static program
+    // (every value is warp-uniform), one elected lane issues
+    const uint32_t leader = elect_one() ? 1u : 0u;
+    uint32_t stage = 0, phase = 0, rdy_phase = 0;
+    long long* itrace = (blockIdx.x == 0 && a.trace != nullptr && leader) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
+    int itrace_n = 0;
+    auto imark = [&]() { if (itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
+    auto wait_rdy = [&]() { imark(); mbar_wait(rdy, rdy_phase); rdy_phase ^= 1; tc_fence_after(); imark(); };
+    auto w_acquire = [&]() -> uint32_t { mbar_wait(full0 + 8 * stage, phase); tc_fence_after(); return sbase + OFF_W + stage * WBLK_BYTES; };
+    auto w_release = [&]() { umma_commit(empty0 + 8 * stage, leader); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } };
+    const uint32_t tb = tmem_base;
+    const uint32_t ones_lo = desc_lo(sbase + OFF_ONES, A_LBO);
+    constexpr uint32_t kHiK = desc_hi(128);          // K-major operands of every kind: 8-row groups 128 B apart
+    constexpr uint32_t kHiActMn = desc_hi(A_LBO);    // activations as MN-major B: 8-channel groups one chunk column apart
+    constexpr uint32_t kN96 = idesc_f16(96, false), kN96Mn = idesc_f16(96, true), kN128 = idesc_f16(128, false), kN32Mn = idesc_f16(32, true),
+                       kN16 = idesc_f16(16, false);
+    // D[:, dcol..dcol+96) (+)= block a_blk [128 x 96] * W^T
+    auto gemm = [&](uint32_t wa, int a_blk, uint32_t dcol, uint32_t accumulate) {
+      const uint32_t a_lo = desc_lo(sbase + OFF_A + a_blk * ABLK_BYTES, A_LBO), b_lo = desc_lo(wa, W_LBO);
 #pragma unroll
-        for (int ks = 0; ks < 6; ++ks)
-          umma_f16(tmem_base + dcol, make_desc(aa + ks * 2 * A_LBO, A_LBO, A_SBO), make_desc(wa + ks * 2 * W_LBO, W_LBO, W_SBO), kIdescN96,
-                   (accumulate || ks > 0) ? 1u : 0u);
-      };
-      auto bias = [&](uint32_t wa, uint32_t dcol) {
-        umma_f16(tmem_base + dcol, make_desc(ones, A_LBO, A_SBO), make_desc(wa + 12 * W_LBO, W_LBO, W_SBO), kIdescN96, 1u);
-      };
-      // D[:, dcol..dcol+96) (+)= blockdiag_p(G) * block b_blk, G = tall operand `which`
-      auto aggregate = [&](int which, int b_blk, uint32_t dcol, bool accumulate) {
-        const uint32_t ta = sbase + OFF_TALL + which * TALL_BYTES, ba = sbase + OFF_A + b_blk * ABLK_BYTES;
+      for (int ks = 0; ks < 6; ++ks)
+        umma_ss(tb + dcol, a_lo + ks * (2 * A_LBO >> 4), kHiK, b_lo + ks * (2 * W_LBO >> 4), kHiK, kN96, (ks > 0) ? 1u : accumulate, leader);
+    };
+    auto bias = [&](uint32_t wa, uint32_t dcol) {
+      umma_ss(tb + dcol, ones_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
+    };
+    // D[:, dcol..dcol+96) (+)= blockdiag_p(G) * block b_blk, G = tall operand `which`
+    auto aggregate = [&](int which, int b_blk, uint32_t dcol, uint32_t accumulate) {
+      uint32_t a_lo = desc_lo(sbase + OFF_TALL + which * TALL_BYTES + 128 * 16, T_LBO);
+      uint32_t b_lo = desc_lo(sbase + OFF_A + b_blk * ABLK_BYTES, 128);
+      uint32_t acc = accumulate;
+#pragma unroll 1
+      for (int p = 0; p < TP; ++p) {
+        umma_ss(tb + dcol, a_lo, kHiK, b_lo, kHiActMn, kN96Mn, acc, leader);
+        umma_ss(tb + dcol, a_lo + (2 * T_LBO >> 4), kHiK, b_lo + 16, kHiActMn, kN96Mn, 1u, leader);
+        acc = 1u;
+        a_lo -= NP;      // window start moves up 17 rows (16 B each, >> 4)
+        b_lo += NP;      // activations of the next pose
+      }
+    };
+    // S_h[:, 0..128) = Q_h K_h^T; Q = block 0, K = block 1, chunk columns 3h..3h+2 (the 4th one of the second K step is
+    // the zero chunk column behind the ones slab for Q, whatever follows for K)
+    auto scores_head = [&](int h, uint32_t dcol) {
+      const uint32_t qa = sbase + OFF_A + 3 * h * A_LBO, ka = qa + ABLK_BYTES;
+      umma_ss(tb + dcol, desc_lo(qa, A_LBO), kHiK, desc_lo(ka, A_LBO), kHiK, kN128, 0u, leader);
+      umma_ss(tb + dcol, desc_lo(qa + 2 * A_LBO, (sbase + OFF_ONES + A_LBO) - (qa + 2 * A_LBO)), kHiK, desc_lo(ka + 2 * A_LBO, A_LBO), kHiK, kN128,
+              1u, leader);
+    };
+    // O[:, 24h..24h+32) = P_h V[:, 24h..24h+32): P_h in TMEM at pcol (64 packed columns), V = block 2 (MN-major)
+    auto pv_head = [&](int h, uint32_t pcol) {
+      const uint32_t b_lo = desc_lo(sbase + OFF_A + 2 * ABLK_BYTES + 3 * h * A_LBO, 128);
 #pragma unroll
-        for (int p = 0; p < TP; ++p)
+      for (int ks = 0; ks < 8; ++ks) umma_ts(tb + COL_O + 24 * h, tb + pcol + 8 * ks, b_lo + ks * 16, kHiActMn, kN32Mn, ks > 0 ? 1u : 0u, leader);
+    };
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int step = 0; step < a.n_steps; ++step) {
+        uint32_t wa;
+        // 0. x = [x_t | T1 x_t | T2 x_t] Win + b at hi/lo precision: A = block 0 chunk columns 0..5 (hi, lo, hi),
+        //    B = [Win_hi ; Win_hi ; Win_lo] (row 15 of each slab carries the bias)
+        wait_rdy();
+        wa = w_acquire();
+        {
+          const uint32_t a_lo = desc_lo(sbase + OFF_A, A_LBO), b_lo = desc_lo(wa, W_LBO);
 #pragma unroll
-          for (int s = 0; s < 2; ++s)
-            umma_f16(tmem_base + dcol, make_desc(ta + (128 - NP * p) * 16 + s * 2 * T_LBO, T_LBO, 128),
-                     make_desc(ba + (NP * p + 16 * s) * 16, 128, A_LBO), kIdescN96BMn, (accumulate || p > 0 || s > 0) ? 1u : 0u);
-      };
-      // S_h[:, 0..128) = Q_h K_h^T; Q = block 0, K = block 1, chunk columns 3h..3h+2 (the 4th one of the second K step is
-      // the zero chunk column behind the ones slab for Q, whatever follows for K)
-      auto scores_head = [&](int h, uint32_t dcol) {
-        const uint32_t qa = sbase + OFF_A + 3 * h * A_LBO, ka = sbase + OFF_A + ABLK_BYTES + 3 * h * A_LBO;
-        umma_f16(tmem_base + dcol, make_desc(qa, A_LBO, A_SBO), make_desc(ka, A_LBO, A_SBO), kIdescN128, 0u);
-        umma_f16(tmem_base + dcol, make_desc(qa + 2 * A_LBO, (sbase + OFF_ONES + A_LBO) - (qa + 2 * A_LBO), A_SBO),
-                 make_desc(ka + 2 * A_LBO, A_LBO, A_SBO), kIdescN128, 1u);
-      };
-      // O[:, 24h..24h+32) = P_h V[:, 24h..24h+32): P_h in TMEM at pcol (64 packed columns), V = block 2 (MN-major)
-      auto pv_head = [&](int h, uint32_t pcol) {
-        const uint32_t va = sbase + OFF_A + 2 * ABLK_BYTES + 3 * h * A_LBO;
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          umma_f16_ts(tmem_base + COL_O + 24 * h, tmem_base + pcol + 8 * ks, make_desc(va + ks * 256, 128, A_LBO), kIdescN32BMn, ks > 0 ? 1u : 0u);
-      };
-      for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
-        for (int step = 0; step < a.n_steps; ++step)
-          for (int l = 0; l < L; ++l) {
-            uint32_t wa;
-            // 1. q, k, v = LN0(x) W + b                         A = block 2
+          for (int ks = 0; ks < 3; ++ks)
+            umma_ss(tb + COL_X, a_lo + ks * (2 * A_LBO >> 4), kHiK, b_lo + ks * (2 * W_LBO >> 4), kHiK, kN96, ks > 0 ? 1u : 0u, leader);
+        }
+        w_release();
+        umma_commit(accb, leader);
+        for (int l = 0; l < L; ++l) {
+          // 1. q, k, v = LN0(x) W + b                         A = block 2
+          wait_rdy();
+          for (int part = 0; part < 3; ++part) { wa = w_acquire(); gemm(wa, 2, COL_ACC + 96 * part, 0u); bias(wa, COL_ACC + 96 * part); w_release(); }
+          umma_commit(accb, leader);
+          // 1b. attention, two heads at a time: S = Q_h K_h^T (d_k = 24 = K step of 16 + 8 real | 8 zero columns),
+          //     softmax on the compute warps (P back into TMEM), O_h = P V_h with V as an MN-major operand
+          for (int pair = 0; pair < 3; ++pair) {
             wait_rdy();
-            for (int part = 0; part < 3; ++part) { wa = w_acquire(); gemm(wa, 2, COL_ACC + 96 * part, false); bias(wa, COL_ACC + 96 * part); w_release(); }
-            umma_commit(accb);
-            // 1b. attention, two heads at a time: S = Q_h K_h^T (d_k = 24 = K step of 16 + 8 real | 8 zero columns),
-            //     softmax on the compute warps (P back into TMEM), O_h = P V_h with V as an MN-major operand
-            for (int pair = 0; pair < 3; ++pair) {
-              wait_rdy();
-              if (pair > 0)
-                for (int e = 0; e < 2; ++e) pv_head(2 * (pair - 1) + e, e ? COL_S1 : COL_S0);
-              if (pair < 2)
-                for (int e = 0; e < 2; ++e) scores_head(2 * pair + e, e ? COL_S1 : COL_S0);
-              umma_commit(accb);
-            }
-            // 2. x += attn Wo + bo                              A = block 0
-            wait_rdy();
-            wa = w_acquire(); gemm(wa, 0, COL_X, true); bias(wa, COL_X); w_release();
-            umma_commit(accb);
-            // 3. g1 = L^ LN1(x)                                 B = block 0
-            wait_rdy();
-            aggregate(2, 0, COL_ACC, false);
-            umma_commit(accb);
-            // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1
-            wait_rdy();
-            for (int part = 0; part < 2; ++part) { wa = w_acquire(); gemm(wa, 1, COL_ACC + 96 * part, false); bias(wa, COL_ACC + 96 * part); w_release(); }
-            umma_commit(accb);
-            // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2
-            wait_rdy();
-            wa = w_acquire(); gemm(wa, 0, COL_ACC, false); bias(wa, COL_X); w_release();
-            wa = w_acquire(); gemm(wa, 2, COL_ACC, true); w_release();
-            umma_commit(accb);
-            // 6. x += L^ z                                      B = block 1
-            wait_rdy();
-            aggregate(2, 1, COL_X, true);
-            umma_commit(accb);
-            // 7. [T1 x | T2 x]                                  B = block 0
-            wait_rdy();
-            aggregate(0, 0, COL_ACC, false);
-            aggregate(1, 0, COL_ACC + 96, false);
-            umma_commit(accb);
-            // 8. c1 = [x | T1 x | T2 x] Wc1 + b                 A = blocks 0, 1, 2
-            wait_rdy();
-            wa = w_acquire(); gemm(wa, 0, COL_ACC, false); bias(wa, COL_ACC); w_release();
-            wa = w_acquire(); gemm(wa, 1, COL_ACC, true); w_release();
-            wa = w_acquire(); gemm(wa, 2, COL_ACC, true); w_release();
-            umma_commit(accb);
-            // 9. [T1 h1 | T2 h1]                                B = block 0
-            wait_rdy();
-            aggregate(0, 0, COL_ACC, false);
-            aggregate(1, 0, COL_ACC + 96, false);
-            umma_commit(accb);
-            // 10. c2 = [h1 | T1 h1 | T2 h1] Wc2 + b             A = blocks 0, 1, 2
-            wait_rdy();
-            wa = w_acquire(); gemm(wa, 0, COL_ACC, false); bias(wa, COL_ACC); w_release();
-            wa = w_acquire(); gemm(wa, 1, COL_ACC, true); w_release();
-            wa = w_acquire(); gemm(wa, 2, COL_ACC, true); w_release();
-            umma_commit(accb);
+            if (pair > 0)
+              for (int e = 0; e < 2; ++e) pv_head(2 * (pair - 1) + e, e ? COL_S1 : COL_S0);
+            if (pair < 2)
+              for (int e = 0; e < 2; ++e) scores_head(2 * pair + e, e ? COL_S1 : COL_S0);
+            umma_commit(accb, leader);
           }
-    }
+          // 2. x += attn Wo + bo                              A = block 0
+          wait_rdy();
+          wa = w_acquire(); gemm(wa, 0, COL_X, 1u); bias(wa, COL_X); w_release();
+          umma_commit(accb, leader);
+          // 3. g1 = L^ LN1(x)                                 B = block 0
+          wait_rdy();
+          aggregate(2, 0, COL_ACC, 0u);
+          umma_commit(accb, leader);
+          // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1
+          wait_rdy();
+          for (int part = 0; part < 2; ++part) { wa = w_acquire(); gemm(wa, 1, COL_ACC + 96 * part, 0u); bias(wa, COL_ACC + 96 * part); w_release(); }
+          umma_commit(accb, leader);
+          // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2
+          wait_rdy();
+          wa = w_acquire(); gemm(wa, 0, COL_ACC, 0u); bias(wa, COL_X); w_release();
+          wa = w_acquire(); gemm(wa, 2, COL_ACC, 1u); w_release();
+          umma_commit(accb, leader);
+          // 6. x += L^ z                                      B = block 1
+          wait_rdy();
+          aggregate(2, 1, COL_X, 1u);
+          umma_commit(accb, leader);
+          // 7. [T1 x | T2 x]                                  B = block 0
+          wait_rdy();
+          aggregate(0, 0, COL_ACC, 0u);
+          aggregate(1, 0, COL_ACC + 96, 0u);
+          umma_commit(accb, leader);
+          // 8. c1 = [x | T1 x | T2 x] Wc1 + b                 A = blocks 0, 1, 2
+          wait_rdy();
+          wa = w_acquire(); gemm(wa, 0, COL_ACC, 0u); bias(wa, COL_ACC); w_release();
+          wa = w_acquire(); gemm(wa, 1, COL_ACC, 1u); w_release();
+          wa = w_acquire(); gemm(wa, 2, COL_ACC, 1u); w_release();
+          umma_commit(accb, leader);
+          // 9. [T1 h1 | T2 h1]                                B = block 0
+          wait_rdy();
+          aggregate(0, 0, COL_ACC, 0u);
+          aggregate(1, 0, COL_ACC + 96, 0u);
+          umma_commit(accb, leader);
+          // 10. c2 = [h1 | T1 h1 | T2 h1] Wc2 + b             A = blocks 0, 1, 2
+          wait_rdy();
+          wa = w_acquire(); gemm(wa, 0, COL_ACC, 0u); bias(wa, COL_ACC); w_release();
+          wa = w_acquire(); gemm(wa, 1, COL_ACC, 1u); w_release();
+          wa = w_acquire(); gemm(wa, 2, COL_ACC, 1u); w_release();
+          umma_commit(accb, leader);
+        }
+        // 11. U = [X_hi | X_lo | X_hi] [Wout_hi ; Wout_hi ; Wout_lo]   (N = 16: 3 Chebyshev orders x 5 outputs)
+        wait_rdy();
+        wa = w_acquire();
+        {
+          const uint32_t b_lo = desc_lo(wa, OUT_LBO);
+#pragma unroll
+          for (int part = 0; part < 3; ++part) {
+            const uint32_t a_lo = desc_lo(sbase + OFF_A + (part == 1 ? ABLK_BYTES : 0), A_LBO);
+#pragma unroll
+            for (int ks = 0; ks < 6; ++ks)
+              umma_ss(tb + COL_ACC, a_lo + ks * (2 * A_LBO >> 4), kHiK, b_lo + (part * 6 + ks) * (2 * OUT_LBO >> 4), kHiK, kN16,
+                      (part | ks) ? 1u : 0u, leader);
+          }
+        }
+        w_release();
+        umma_commit(accb, leader);
+      }
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- compute warps
@@ -565,8 +656,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     c.trace_n = 0; c.trace_cap = a.trace_cap / 2;
     const int row = c.row, hh = c.hh;
     float* scratch = reinterpret_cast<float*>(smem + OFF_A);   // [128][16] fp32, aliases the head of operand block 0
-    const float* temb_s = reinterpret_cast<const float*>(smem + OFF_TE);
     const bool has_mask = a.mask != nullptr;
+    uint32_t ps = 0, pphase = 0;                               // parameter stage of the current layer
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
@@ -585,56 +676,51 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       bar_compute();
 
       for (int step = 0; step < a.n_steps; ++step) {
-        // ---- input ChebConv (K = 15): fp32 on the CUDA cores.  scratch[row][0:15] = [x | T1 x | T2 x]
-        for (int idx = tid; idx < TM * 5; idx += kComputeThreads) {
-          const int r = idx / 5, cc = idx - r * 5;
-          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        // ---- input ChebConv (ChebConv.py:74-88, K = 15): the panel [x | T1 x | T2 x | 1] of every row, split into
+        //      fp16 hi and lo parts, becomes chunk columns 0..5 of operand block 0 (hi, lo, hi)
+        if (tid < TM) {
+          const int r = tid;
+          float pv[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pv[i] = 0.f;
           if (r < TR) {
             const int p = r / NP, i = r - p * NP;
-            v0 = xt[r * 8 + cc];
+#pragma unroll
+            for (int cc = 0; cc < 5; ++cc) pv[cc] = xt[r * 8 + cc];
 #pragma unroll
             for (int n = 0; n < NNB; ++n) {
-              const float u = xt[(p * NP + nbi[i * NNB + n]) * 8 + cc];
+              const float* u = xt + (p * NP + nbi[i * NNB + n]) * 8;
               const float2 cf = nbc[i * NNB + n];
-              v1 = fmaf(cf.x, u, v1);
-              v2 = fmaf(cf.y, u, v2);
+#pragma unroll
+              for (int cc = 0; cc < 5; ++cc) { pv[5 + cc] = fmaf(cf.x, u[cc], pv[5 + cc]); pv[10 + cc] = fmaf(cf.y, u[cc], pv[10 + cc]); }
             }
           }
-          scratch[r * 16 + cc] = v0; scratch[r * 16 + 5 + cc] = v1; scratch[r * 16 + 10 + cc] = v2;
+          pv[15] = 1.0f;      // multiplies the bias row of the weight slabs
+          uint4 h0, l0, h1, l1;
+          split8(pv, h0, l0);
+          split8(pv + 8, h1, l1);
+          uint8_t* dst = smem + OFF_A;
+          *reinterpret_cast<uint4*>(dst + a_chunk(r, 0)) = h0; *reinterpret_cast<uint4*>(dst + a_chunk(r, 1)) = h1;
+          *reinterpret_cast<uint4*>(dst + a_chunk(r, 2)) = l0; *reinterpret_cast<uint4*>(dst + a_chunk(r, 3)) = l1;
+          *reinterpret_cast<uint4*>(dst + a_chunk(r, 4)) = h0; *reinterpret_cast<uint4*>(dst + a_chunk(r, 5)) = h1;
         }
-        bar_compute();
-        {
-          float accv[48];
-#pragma unroll
-          for (int g = 0; g < 12; ++g) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.bin + hh * 48) + g);
-            accv[4 * g] = b4.x; accv[4 * g + 1] = b4.y; accv[4 * g + 2] = b4.z; accv[4 * g + 3] = b4.w;
-          }
-          for (int k = 0; k < 15; ++k) {
-            const float bv = scratch[row * 16 + k];
-#pragma unroll
-            for (int g = 0; g < 12; ++g) {
-              const float4 w4 = __ldg(reinterpret_cast<const float4*>(w.win + k * H + hh * 48) + g);
-              accv[4 * g] = fmaf(bv, w4.x, accv[4 * g]); accv[4 * g + 1] = fmaf(bv, w4.y, accv[4 * g + 1]);
-              accv[4 * g + 2] = fmaf(bv, w4.z, accv[4 * g + 2]); accv[4 * g + 3] = fmaf(bv, w4.w, accv[4 * g + 3]);
-            }
-          }
-          tmem_st48(c.tmem_lane + COL_X + hh * 48, accv);
-        }
-        bar_compute();
-        // the scratch rows covered the 16-byte skew gaps of operand block 0: they are read (times zero) by the MN-major
-        // aggregation operands, so they must hold finite fp16 again
-        if (tid < 4) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
+        signal_ready(c);                                           // -> 0
+        wait_acc(c);
+        float v[48];
+        tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
 
         for (int l = 0; l < L; ++l) {
-          const LayerW& Lw = w.layer[l];
-          // this layer's L^ into the tall operand, this (step, layer)'s temb into shared memory
-          for (int i = tid; i < NP * NP; i += kComputeThreads) *tall_elem(smem, 2, 128 + i / NP, i % NP) = __float2half_rn(__ldg(Lw.lhat + i));
-          if (tid < H) reinterpret_cast<float*>(smem + OFF_TE)[tid] = __ldg(a.temb + ((size_t)step * L + l) * H + tid);
-          float v[48];
+          // this layer's parameters (LayerNorm gains, L^, temb) have been staged by the producer
+          mbar_wait(pfull0 + 8 * ps, pphase);
+          const uint8_t* par = smem + OFF_PAR + ps * PAR_BYTES;
+          const float* lnp = reinterpret_cast<const float*>(par);
+          const float* temb_s = reinterpret_cast<const float*>(par + LP_BYTES);
+          if (tid < 4 * NP) {   // L^ into rows 128..144 of its tall operand
+            const int kc = tid / NP, r = tid - kc * NP;
+            *reinterpret_cast<uint4*>(smem + OFF_TALL + 2 * TALL_BYTES + kc * T_LBO + (128 + r) * 16) = *reinterpret_cast<const uint4*>(par + LP_LN_BYTES + tid * 16);
+          }
           // ======== x = x + attn(LN0(x))
-          tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
-          layer_norm_rows(c, v, Lw.ln0_a, Lw.ln0_b);
+          layer_norm_rows(c, v, lnp, lnp + H);
           store_half_row(c, 2, v);
           signal_ready(c);                                         // -> 1
           wait_acc(c);
@@ -661,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c);
           // ======== x = x + GraphNet(LN1(x))
           tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
-          layer_norm_rows(c, v, Lw.ln1_a, Lw.ln1_b);
+          layer_norm_rows(c, v, lnp + 2 * H, lnp + 3 * H);
           store_half_row(c, 0, v);
           signal_ready(c);                                         // -> 3
           wait_acc(c);
@@ -685,6 +771,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);                                         // -> 8
           wait_acc(c);
           epi_group<2>(c, COL_ACC, 0, temb_s);
+          // last use of this layer's parameters: hand the stage back to the producer
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pempty0 + 8 * ps);
+          if (++ps == 2) { ps = 0; pphase ^= 1; }
           signal_ready(c);                                         // -> 9
           wait_acc(c);
           epi_group<0>(c, COL_ACC, 1, nullptr);
@@ -700,67 +790,62 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             launder<48>(u);
 #pragma unroll
             for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);
-            tmem_st48(c.tmem_lane + COL_X + hh * 48, v);
+            if (l + 1 < L) tmem_st48(c.tmem_lane + COL_X + hh * 48, v);   // v stays in registers for the next LayerNorm
           }
         }
 
-        // ---- output ChebConv (N = 5): U_k = X Wout_k on the CUDA cores, then eps = b + U0 + T1 U1 + T2 U2
+        // ---- output ChebConv (N = 5): U_k = X Wout_k on the tensor cores with X = hi + lo, then
+        //      eps = b + U0 + T1 U1 + T2 U2 and the DDIM update on the CUDA cores
         {
-          float v[48];
-          tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
-          float accv[15];
+          uint8_t* d0 = smem + OFF_A;
 #pragma unroll
-          for (int i = 0; i < 15; ++i) accv[i] = 0.f;
-#pragma unroll
-          for (int e = 0; e < 48; ++e) {
-            const int ch = hh * 48 + e;
-#pragma unroll
-            for (int k3 = 0; k3 < 3; ++k3)
-#pragma unroll
-              for (int n = 0; n < 5; ++n) accv[k3 * 5 + n] = fmaf(v[e], __ldg(w.wout + (k3 * H + ch) * 5 + n), accv[k3 * 5 + n]);
-          }
-          bar_compute();   // every warp is past its last use of operand block 0 as an MMA operand (wait_acc above) -- scratch is free
-          if (hh == 1) {
-#pragma unroll
-            for (int i = 0; i < 15; ++i) scratch[row * 16 + i] = accv[i];
-          }
-          bar_compute();
-          if (hh == 0) {
-#pragma unroll
-            for (int i = 0; i < 15; ++i) scratch[row * 16 + i] += accv[i];
+          for (int q = 0; q < 6; ++q) {
+            uint4 hi, lo;
+            split8(v + 8 * q, hi, lo);
+            *reinterpret_cast<uint4*>(d0 + a_chunk(row, hh * 6 + q)) = hi;
+            *reinterpret_cast<uint4*>(d0 + ABLK_BYTES + a_chunk(row, hh * 6 + q)) = lo;
           }
         }
-        bar_compute();
-        for (int idx = tid; idx < TR * 5; idx += kComputeThreads) {
-          const int r = idx / 5, n = idx - r * 5;
-          const int p = r / NP, i = r - p * NP;
-          float v = __ldg(w.bout + n) + scratch[r * 16 + n];
+        signal_ready(c);                                           // -> 11
+        wait_acc(c);
+        if (hh == 0) {
+          float u[16];
+          tmem_ld16_async(c.tmem_lane + COL_ACC, u);
+          tmem_ld_wait();
+          launder<16>(u);
 #pragma unroll
-          for (int q = 0; q < NNB; ++q) {
-            const int rj = p * NP + nbi[i * NNB + q];
-            const float2 cf = nbc[i * NNB + q];
-            v = fmaf(cf.x, scratch[rj * 16 + 5 + n], v);
-            v = fmaf(cf.y, scratch[rj * 16 + 10 + n], v);
-          }
-          ep[r * 8 + n] = v;
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(scratch + row * 16 + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
         }
+        tc_fence_before();
         bar_compute();
-        // ---- DDIM update (common/utils_diff.py:59-65), same operation order, no FMA contraction
+        // eps and the DDIM update (common/utils_diff.py:59-65), same operation order, no FMA contraction
         {
           const dp_step st = a.steps_dev ? a.steps_dev[step] : inl.s[step];
           for (int idx = tid; idx < R * 5; idx += kComputeThreads) {
-            const int r = idx / 5, cc = idx - r * 5;
-            const float et = ep[r * 8 + cc], xv = xt[r * 8 + cc];
+            const int r = idx / 5, n = idx - r * 5;
+            const int p = r / NP, i = r - p * NP;
+            float et = __ldg(w.bout + n) + scratch[r * 16 + n];
+#pragma unroll
+            for (int q = 0; q < NNB; ++q) {
+              const int rj = p * NP + nbi[i * NNB + q];
+              const float2 cf = nbc[i * NNB + q];
+              et = fmaf(cf.x, scratch[rj * 16 + 5 + n], et);
+              et = fmaf(cf.y, scratch[rj * 16 + 10 + n], et);
+            }
+            const float xv = xt[r * 8 + n];
             const float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(et, st.sqrt_1m_at)), st.sqrt_at);
             float nx = __fmul_rn(st.sqrt_an, x0);
             if (a.noise) {
               const float z = a.noise[((size_t)step * a.n_rows + g0) * NP * 5 + idx];
               nx = __fadd_rn(nx, __fmul_rn(st.c1, z));
             }
-            xt[r * 8 + cc] = __fadd_rn(nx, __fmul_rn(st.c2, et));
+            xt[r * 8 + n] = __fadd_rn(nx, __fmul_rn(st.c2, et));
           }
         }
         bar_compute();
+        // the scratch rows covered the 16-byte skew gaps of operand block 0: they are read (times zero) by the MN-major
+        // aggregation operands, so they must hold finite fp16 again
+        if (tid < 4) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
       }
       for (int idx = tid; idx < R * 5; idx += kComputeThreads) a.out[(size_t)g0 * NP * 5 + idx] = xt[(idx / 5) * 8 + idx % 5];
       bar_compute();
@@ -786,10 +871,50 @@ __global__ void tc2_pack_block_kernel(uint8_t* __restrict__ dst, const float* __
   }
 }
 
+__device__ __forceinline__ float hi16(float v) { return __half2float(__float2half_rn(v)); }
+
+// Input convolution block [N=96][K=48]: K slabs [hi ; hi ; lo] of the panel weights Win [15][96] with the bias in row 15.
+// Output convolution block [N=16][K=288] (K-adjacent core matrices OUT_LBO apart): slabs [hi ; hi ; lo] of Wout
+// reshaped to [96][3*5] (column = order*5 + output), column 15 zero.  Both blocks are zero padded to WBLK_BYTES.
+__global__ void tc2_pack_io_kernel(uint8_t* __restrict__ dst, const float* __restrict__ win, const float* __restrict__ bin,
+                                   const float* __restrict__ wout) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 96 * 48; idx += gridDim.x * blockDim.x) {
+    const int n = idx / 48, k = idx - n * 48;
+    const int slab = k >> 4, kk = k & 15;
+    const float full = kk < 15 ? win[kk * 96 + n] : bin[n];
+    const float v = slab < 2 ? hi16(full) : full - hi16(full);
+    const size_t off = (size_t)(k >> 3) * W_LBO + (size_t)(n >> 3) * W_SBO + (n & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
+  }
+  uint8_t* d2 = dst + WBLK_BYTES;
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 16 * 288; idx += gridDim.x * blockDim.x) {
+    const int n = idx / 288, k = idx - n * 288;
+    const int slab = k / 96, ch = k - slab * 96;
+    float full = 0.f;
+    if (n < 15) full = wout[((n / 5) * 96 + ch) * 5 + (n % 5)];
+    const float v = slab < 2 ? hi16(full) : full - hi16(full);
+    const size_t off = (size_t)(k >> 3) * OUT_LBO + (size_t)(n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(d2 + off) = __float2half_rn(v);
+  }
+}
+
+// per-layer parameter record: ln0_a, ln0_b, ln1_a, ln1_b (fp32) then L^ as fp16 [4 chunk columns][17 rows][8]
+__global__ void tc2_pack_lparams_kernel(uint8_t* __restrict__ dst, const float* ln0a, const float* ln0b, const float* ln1a, const float* ln1b,
+                                        const float* __restrict__ lhat) {
+  float* f = reinterpret_cast<float*>(dst);
+  for (int i = threadIdx.x; i < H; i += blockDim.x) { f[i] = ln0a[i]; f[H + i] = ln0b[i]; f[2 * H + i] = ln1a[i]; f[3 * H + i] = ln1b[i]; }
+  __half* hp = reinterpret_cast<__half*>(dst + LP_LN_BYTES);
+  for (int i = threadIdx.x; i < 4 * NP * 8; i += blockDim.x) {
+    const int kc = i / (NP * 8), r = (i / 8) % NP, e = i & 7;
+    const int k = kc * 8 + e;
+    hp[i] = __float2half_rn(k < NP ? lhat[r * NP + k] : 0.f);
+  }
+}
+
 }  // namespace
 
 struct Tc2Pack {
-  uint8_t* blocks = nullptr;   // [n_layer][14][WBLK_BYTES]
+  uint8_t* blocks = nullptr;   // [n_layer][14][WBLK_BYTES] then [2][WBLK_BYTES] (io blocks) then [n_layer][LP_BYTES]
   size_t bytes = 0;
 };
 
@@ -812,13 +937,15 @@ static int pack_block(uint8_t* dst, const float* W, int ldw, int k0, int n0, con
 int tc2_pack(dp_model* m, cudaStream_t s) {
   const Dims& d = m->d;
   if (!m->tc2) m->tc2 = new Tc2Pack();
-  const size_t need = (size_t)d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
+  const size_t wbytes = (size_t)d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
+  const size_t need = wbytes + 2 * WBLK_BYTES + (size_t)d.n_layer * LP_BYTES;
   if (m->tc2->bytes < need) {
     if (m->tc2->blocks) cudaFree(m->tc2->blocks);
     m->tc2->blocks = nullptr; m->tc2->bytes = 0;
     DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc2->blocks), need));
     m->tc2->bytes = need;
   }
+  DP_CUDA(cudaMemsetAsync(m->tc2->blocks, 0, need, s));
   for (int l = 0; l < d.n_layer; ++l) {
     const LayerW& L = m->hw.layer[l];
     uint8_t* b = m->tc2->blocks + (size_t)l * BLOCKS_PER_LAYER * WBLK_BYTES;
@@ -831,7 +958,13 @@ int tc2_pack(dp_model* m, cudaStream_t s) {
     for (int part = 0; part < 2; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.w2, H, part * H, 0, part == 0 ? L.b2 : nullptr, s));
     for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wc1, H, part * H, 0, part == 0 ? L.bc1 : nullptr, s));
     for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wc2, H, part * H, 0, part == 0 ? L.bc2 : nullptr, s));
+    tc2_pack_lparams_kernel<<<1, 128, 0, s>>>(m->tc2->blocks + wbytes + 2 * WBLK_BYTES + (size_t)l * LP_BYTES, L.ln0_a, L.ln0_b, L.ln1_a, L.ln1_b, L.lhat);
+    count_launch();
+    DP_CUDA(cudaGetLastError());
   }
+  tc2_pack_io_kernel<<<18, 256, 0, s>>>(m->tc2->blocks + wbytes, m->hw.win, m->hw.bin, m->hw.wout);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
   return DP_OK;
 }
 
@@ -844,8 +977,10 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
     DP_CUDA(cudaFuncSetAttribute(tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
+  const size_t wbytes = (size_t)m->d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
   Tc2Args a{};
-  a.w = m->dw; a.wpack = m->tc2->blocks; a.n_layer = m->d.n_layer; a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
+  a.w = m->dw; a.wpack = m->tc2->blocks; a.ioblocks = m->tc2->blocks + wbytes; a.lparams = m->tc2->blocks + wbytes + 2 * WBLK_BYTES;
+  a.n_layer = m->d.n_layer; a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
   a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_steps = n_steps; a.temb = m->temb; a.noise = noise; a.mask = mask;
   a.steps_dev = steps_dev;
   a.trace = m->trace; a.trace_cap = m->trace_cap;

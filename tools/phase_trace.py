@@ -44,28 +44,13 @@ def main():
     it = full[buf.numel() // 2:]
     it = it[it > 0]          # issuer: (before wait_rdy = all MMAs of the previous group issued, after wait_rdy) pairs
     n_layers, n_steps = 5, 2
-    per_layer = len(t) // (n_layers * n_steps)
-    print(f"{len(t)} stamps, {per_layer} per layer; total {t[-1] - t[0]} cycles for {n_steps} steps x {n_layers} layers")
-    d = np.diff(t)
-    # stamps alternate S, A, S, A ... within a layer; between layers (A_last -> S_first of the next layer) is an epilogue
-    lay = t[: per_layer * n_layers * n_steps].reshape(n_steps * n_layers, per_layer)
+    per_step = len(t) // n_steps                      # 2 (input conv) + 26 per layer + 2 (output conv)
+    per_layer = (per_step - 4) // n_layers
+    print(f"{len(t)} stamps, {per_step} per step, {per_layer} per layer; total {t[-1] - t[0]} cycles for {n_steps} steps x {n_layers} layers")
+    steps = t[: per_step * n_steps].reshape(n_steps, per_step)
+    lay = steps[:, 2:2 + per_layer * n_layers].reshape(n_steps * n_layers, per_layer)
     seg = np.diff(lay, axis=1)                     # [layers][per_layer-1]
-    tail = np.r_[lay[1:, 0] - lay[:-1, -1], np.nan]   # epilogue that crosses into the next layer (incl. step boundary work)
     mean = seg[1:].mean(axis=0)                    # skip the very first layer (cold)
-    names = args.names.split(",") if args.names else []
-    # issuer view of each hand-over k (same order as the compute stamps): S_k -> woke -> issued -> A_k
-    npair = min(len(it) // 2, len(t) // 2)
-    woke = it[1:2 * npair:2]                                  # after wait_rdy k
-    issued = np.r_[it[2:2 * npair:2], it[2 * npair - 1]]      # before wait_rdy k+1 = group k fully issued + committed
-    S, A = t[0:2 * npair:2], t[1:2 * npair:2]
-    per = per_layer // 2
-    def lay_mean(x):
-        x = x[: (len(x) // per) * per].reshape(-1, per)[1:]
-        return x.mean(axis=0)
-    sig, iss, drain = lay_mean(woke - S), lay_mean(issued - woke), lay_mean(A - issued)
-    print("  hand-over breakdown per MMA group: signal->issuer awake | issue loop | last issue->accumulator observed")
-    for k in range(per):
-        print(f"    group {k:2d}: {sig[k]:6.0f} | {iss[k]:6.0f} | {drain[k]:6.0f}")
     tot_mma = tot_epi = 0.0
     for i, v in enumerate(mean):
         kind = "MMA+handover" if i % 2 == 0 else "epilogue    "
@@ -73,11 +58,23 @@ def main():
             tot_mma += v
         else:
             tot_epi += v
-        print(f"  {i:2d} {kind} {v:8.0f} cyc  min {seg[1:, i].min():6d} max {seg[1:, i].max():6d}  {names[i] if i < len(names) else ''}")
-    inner = np.array([tail[i] for i in range(len(tail) - 1) if (i + 1) % n_layers != 0])
-    print(f"  layer-crossing epilogue (residual update + LN0 of next layer): {np.nanmean(inner):8.0f} cyc")
-    print(f"  step-crossing (out conv, DDIM update, in conv, LN0): {tail[n_layers - 1]:8.0f} cyc")
-    print(f"  per layer: MMA+handover {tot_mma:.0f}, epilogues {tot_epi + np.nanmean(inner):.0f}, sum {tot_mma + tot_epi + np.nanmean(inner):.0f}")
+        print(f"  {i:2d} {kind} {v:8.0f} cyc  min {seg[1:, i].min():6d} max {seg[1:, i].max():6d}")
+    cross = [lay[i + 1, 0] - lay[i, -1] for i in range(len(lay) - 1) if (i + 1) % n_layers != 0]
+    print(f"  layer-crossing epilogue (residual update + LN0 of next layer): {np.mean(cross):8.0f} cyc")
+    print(f"  per layer: MMA+handover {tot_mma:.0f}, epilogues {tot_epi + np.mean(cross):.0f}, sum {tot_mma + tot_epi + np.mean(cross):.0f}")
+    for s_ in range(n_steps):
+        st = steps[s_]
+        print(f"  step {s_}: in-conv MMA {st[1] - st[0]}, X load + LN0 {st[2] - st[1]}, residual+split {st[-2] - st[-3]}, out-conv MMA {st[-1] - st[-2]}"
+              + (f", eps + DDIM + gather of next step {steps[s_ + 1][0] - st[-1]}" if s_ + 1 < n_steps else ""))
+    # issuer view of each hand-over k (same order as the compute stamps): S_k -> woke -> issued -> A_k
+    npair = min(len(it) // 2, len(t) // 2)
+    woke = it[1:2 * npair:2]
+    issued = np.r_[it[2:2 * npair:2], it[2 * npair - 1]]
+    S, A = t[0:2 * npair:2], t[1:2 * npair:2]
+    k0 = per_step // 2                                # second step
+    print("  hand-over breakdown per MMA group (second step): signal->issuer awake | issue loop | last issue->accumulator observed")
+    for k in range(k0, min(k0 + 1 + per_layer // 2 + 1, npair)):
+        print(f"    group {k - k0:2d}: {woke[k] - S[k]:6d} | {issued[k] - woke[k]:6d} | {A[k] - issued[k]:6d}")
 
 
 if __name__ == "__main__":
