@@ -34,7 +34,9 @@ namespace {
 constexpr int NP = 17;
 constexpr int TM = 128;              // tile rows = UMMA M
 constexpr int TP = 7;                // poses per tile
-constexpr int TR = TP * NP;          // 119 valid rows
+constexpr int PS = 18;               // tile rows per pose: 17 joints + 1 pad row, so every pose starts on an even row and the
+                                     // rows of a warp (32) always begin 0, 14, 10 or 6 rows into a pose -> one softmax code path
+constexpr int TR = TP * PS;          // 126 rows carry poses
 constexpr int H = 96;
 constexpr int NSTAGE = 4;
 constexpr int WK = 112;              // weight block K extent: 96 weights + 16 (bias slab; k=96 hi, k=97 lo)
@@ -241,6 +243,8 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   lo = pack8(r);
 }
 
+#define DP_PHASE_FN __forceinline__
+
 struct Tc2Args {
   const Weights* w;          // fp32 blob (T1/T2 for the gathers, output bias)
   const uint8_t* wpack;      // fp16 weight blocks [n_layer][14][21504 B]
@@ -289,17 +293,32 @@ __device__ __forceinline__ void wait_acc(Ctx& c) {
   trace_mark(c);
 }
 
-// 48 fp32 values of (row, channels 48*hh..) -> fp16 operand block `blk`
-__device__ __forceinline__ void store_half_row(const Ctx& c, int blk, const float* v) {
-  uint8_t* dst = c.smem + OFF_A + blk * ABLK_BYTES;
+// One epilogue group: 48 accumulator columns of this thread's lane: TMEM -> registers -> clamp (0 = relu, -inf = none)
+// -> (+ temb) -> fp16 -> six 16-byte chunks of an operand block.  Deliberately NOT inlined: the layer body calls it 17
+// times, and one copy of the code keeps the loop inside the instruction cache.  All arguments travel in registers
+// (the shared-memory carve-out leaves next to no L1 for a stack).
+__device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb) {
+  float v[48];
+  tmem_ld48(col, v);
+  if (lo == 0.f) {
 #pragma unroll
-  for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + a_chunk(c.row, c.hh * 6 + q)) = pack8(v + 8 * q);
+    for (int i = 0; i < 48; ++i) v[i] = fmaxf(v[i], 0.f);
+  }
+  if (temb != nullptr) {
+#pragma unroll
+    for (int i = 0; i < 48; i += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(temb + i);
+      v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + q * A_LBO) = pack8(v + 8 * q);
 }
 
-// LayerNorm (GraFormer.py:67-70: unbiased std, eps added to std) of the residual row held by threads (row, 0) and
-// (row, 1), 48 channels each; the halves exchange (mean, M2) through shared memory and merge them exactly.
-// ga/gb: shared-memory copies of a_2 / b_2.
-__device__ __forceinline__ void layer_norm_rows(const Ctx& c, float* v, const float* ga, const float* gb) {
+// LayerNorm phase: residual row (48 of its 96 channels per thread) from TMEM -> LayerNorm -> fp16 operand block
+__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, int row, int hh, const float* ga, const float* gb, uint32_t dst_off) {
+  float v[48];
+  tmem_ld48(xcol, v);
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 48; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
@@ -311,104 +330,103 @@ __device__ __forceinline__ void layer_norm_rows(const Ctx& c, float* v, const fl
     q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
   }
   const float qq = (q0 + q1) + (q2 + q3);
-  float2* stat = reinterpret_cast<float2*>(c.smem + OFF_STAT);
-  stat[c.hh * TM + c.row] = make_float2(m, qq);
+  float2* stat = reinterpret_cast<float2*>(smem + OFF_STAT);
+  stat[hh * TM + row] = make_float2(m, qq);
   bar_compute();
-  const float2 o = stat[(c.hh ^ 1) * TM + c.row];
+  const float2 o = stat[(hh ^ 1) * TM + row];
   const float mean = 0.5f * (m + o.x);
   const float dm = m - o.x;
   const float m2 = qq + o.y + dm * dm * 24.0f;
-  const float inv = 1.0f / (sqrtf(m2 * (1.0f / (float)(H - 1))) + 1e-6f);
+  const float inv = __frcp_rn(sqrtf(m2 * (1.0f / (float)(H - 1))) + 1e-6f);
 #pragma unroll
   for (int q = 0; q < 12; ++q) {
-    const float4 a = *reinterpret_cast<const float4*>(ga + c.hh * 48 + 4 * q), b = *reinterpret_cast<const float4*>(gb + c.hh * 48 + 4 * q);
+    const float4 a = *reinterpret_cast<const float4*>(ga + hh * 48 + 4 * q), b = *reinterpret_cast<const float4*>(gb + hh * 48 + 4 * q);
     v[4 * q] = fmaf(a.x * inv, v[4 * q] - mean, b.x); v[4 * q + 1] = fmaf(a.y * inv, v[4 * q + 1] - mean, b.y);
     v[4 * q + 2] = fmaf(a.z * inv, v[4 * q + 2] - mean, b.z); v[4 * q + 3] = fmaf(a.w * inv, v[4 * q + 3] - mean, b.w);
   }
+  uint8_t* dst = smem + dst_off;
+#pragma unroll
+  for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + q * A_LBO) = pack8(v + 8 * q);
 }
 
-// accumulator columns [col0 + 48*hh, +48) -> fp16 operand block.  KIND: 0 plain, 1 relu, 2 relu + temb (smem vector)
-template <int KIND>
-__device__ __forceinline__ void epi_group(const Ctx& c, uint32_t col0, int blk, const float* temb) {
-  float v[48];
-  tmem_ld48(c.tmem_lane + col0 + c.hh * 48, v);
-  if (KIND >= 1) {
+// x += relu(acc): the closing residual of the Chebyshev block, in TMEM
+__device__ DP_PHASE_FN void resid_run(uint32_t xcol, uint32_t acol) {
+  float u[48], v[48];
+  tmem_ld16_async(acol, u);
+  tmem_ld16_async(acol + 16, u + 16);
+  tmem_ld16_async(acol + 32, u + 32);
+  tmem_ld48(xcol, v);
+  launder<48>(u);
 #pragma unroll
-    for (int i = 0; i < 48; ++i) v[i] = fmaxf(v[i], 0.f);
-  }
-  if (KIND == 2) {
-#pragma unroll
-    for (int i = 0; i < 48; i += 4) {
-      const float4 t = *reinterpret_cast<const float4*>(temb + c.hh * 48 + i);
-      v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-    }
-  }
-  store_half_row(c, blk, v);
+  for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);
+  tmem_st48(xcol, v);
 }
 
 // Softmax of one head's scores for this thread's row (GraFormer.py:104-111).  The scores of the whole tile sit in
 // TMEM as S[128 x 128] (row = query, column = key row of the tile); a row only needs the 17 columns of its own pose.
-// The 32 rows of a warp span at most three poses, so the warp loads one window of 48/64 columns and every lane picks
-// its pose's 17 with selects at compile-time offsets.  The probabilities go back to TMEM as fp16 pairs, zero outside the
-// pose (block-diagonal P[128 x 128]), and feed the P V product as its A operand.
-template <int WQ>
-__device__ __forceinline__ void softmax_row(const Ctx& c, uint32_t region, bool has_mask) {
-  constexpr int START = WQ == 0 ? 0 : WQ == 1 ? 16 : WQ == 2 ? 48 : 80;     // first loaded column
-  constexpr int WIN = (WQ == 0 || WQ == 3) ? 48 : 64;                       // loaded columns
-  constexpr int P0 = WQ == 0 ? 0 : WQ == 1 ? 1 : WQ == 2 ? 3 : 5;           // first pose of the warp's rows
-  constexpr int NPOSE = (WQ == 0 || WQ == 3) ? 2 : 3;
-  float v[WIN];
+// Poses start every PS = 18 rows, so the 32 rows of a warp span at most three poses beginning at pose p0 = 32*wq/18:
+// the warp loads the 64 columns from 18*p0 and every lane picks its pose's 17 with selects at compile-time offsets.
+// The probabilities go back to TMEM as fp16 pairs, zero outside the pose (block-diagonal P[128 x 128]), and feed the
+// P V product as its A operand.  One code path for all warps.
+__device__ DP_PHASE_FN void softmax_run(const uint8_t* smem, uint32_t region, int row, bool has_mask) {
+  const int p0 = ((row & ~31) * 57) >> 10;          // (32*wq) / 18 for wq = 0..3  ->  0, 1, 3, 5
+  const int p = min(row / PS, TP - 1);              // pad rows 126, 127 ride along as pose 6
+  const int q = p - p0;
+  float v[64];
 #pragma unroll
-  for (int i = 0; i < WIN; i += 16) tmem_ld16_async(region + START + i, v + i);
+  for (int i = 0; i < 64; i += 16) tmem_ld16_async(region + PS * p0 + i, v + i);
   tmem_ld_wait();
-  launder<WIN>(v);
-  const int q = min(c.row / NP, TP - 1) - P0;      // pad rows 119..127 ride along as pose 6
-  const float* maskf = reinterpret_cast<const float*>(c.smem + OFF_MASK);
+  launder<64>(v);
   const float k2 = 0.20412414523193151f * 1.4426950408889634f;   // log2(e) / sqrt(24): softmax(s / sqrt(d_k)) in base 2
   float sc[NP];
-  float mx = -INFINITY;
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
-    float t = q == 0 ? v[NP * P0 - START + j] : v[NP * (P0 + 1) - START + j];
-    if (NPOSE == 3) t = q == 2 ? v[NP * (P0 + 2) - START + j] : t;
-    if (has_mask) t = maskf[j] == 0.f ? -1e9f * 4.898979485566356f : t;     // masked_fill(-1e9) acts after the 1/sqrt(d_k) scaling
-    sc[j] = t;
-    mx = fmaxf(mx, t);
+    const float t = q == 0 ? v[j] : v[PS + j];
+    sc[j] = q == 2 ? v[2 * PS + j] : t;
   }
-  const float mk = mx * k2;
-  float s0 = 0.f, s1 = 0.f;
+  if (has_mask) {
+    const float* maskf = reinterpret_cast<const float*>(smem + OFF_MASK);
 #pragma unroll
-  for (int j = 0; j < NP; ++j) {
-    sc[j] = ex2(fmaf(sc[j], k2, -mk));
-    if (j & 1) s1 += sc[j]; else s0 += sc[j];
+    for (int j = 0; j < NP; ++j) sc[j] = maskf[j] == 0.f ? -1e9f * 4.898979485566356f : sc[j];   // masked_fill(-1e9) acts after the 1/sqrt(d_k) scaling
   }
-  const float inv = 1.0f / (s0 + s1);
+  float m0 = fmaxf(sc[0], sc[1]), m1 = fmaxf(sc[2], sc[3]), m2 = fmaxf(sc[4], sc[5]), m3 = fmaxf(sc[6], sc[7]);
+  m0 = fmaxf(m0, fmaxf(sc[8], sc[9])); m1 = fmaxf(m1, fmaxf(sc[10], sc[11])); m2 = fmaxf(m2, fmaxf(sc[12], sc[13])); m3 = fmaxf(m3, fmaxf(sc[14], sc[15]));
+  const float mk = fmaxf(fmaxf(m0, m1), fmaxf(fmaxf(m2, m3), sc[16])) * k2;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; j += 4) {
+    sc[j] = ex2(fmaf(sc[j], k2, -mk)); sc[j + 1] = ex2(fmaf(sc[j + 1], k2, -mk));
+    sc[j + 2] = ex2(fmaf(sc[j + 2], k2, -mk)); sc[j + 3] = ex2(fmaf(sc[j + 3], k2, -mk));
+    s0 += sc[j]; s1 += sc[j + 1]; s2 += sc[j + 2]; s3 += sc[j + 3];
+  }
+  sc[16] = ex2(fmaf(sc[16], k2, -mk));
+  const float inv = __frcp_rn((s0 + s1) + (s2 + s3) + sc[16]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) sc[j] *= inv;
-  // K position x of P (x = key row of the tile): pose x/17 (static), joint x%17
-  auto pick = [&](int x) -> float {
-    if (x < NP * P0 || x >= NP * (P0 + NPOSE) || x >= TR) return 0.f;
-    return (q == x / NP - P0) ? sc[x % NP] : 0.f;
-  };
+  // P columns: K position x (= key row of the tile) belongs to pose x / 18, joint x % 18 (17 = pad, probability 0).
+  // The 64 packed columns go out as four pieces of 16; a piece none of the warp's poses touches is all zero.
 #pragma unroll
   for (int piece = 0; piece < 4; ++piece) {
     uint32_t pk[16];
+    const int pa = (32 * piece) / PS, pb = (32 * piece + 31) / PS;      // poses this piece covers (static)
+    if (p0 + 2 >= pa && p0 <= pb) {                                      // warp-uniform
 #pragma unroll
-    for (int i = 0; i < 16; ++i) pk[i] = pack2(pick(32 * piece + 2 * i), pick(32 * piece + 2 * i + 1));
+      for (int i = 0; i < 16; ++i) {
+        const int x0 = 32 * piece + 2 * i, x1 = x0 + 1;
+        const float e0 = (x0 % PS != NP && p == x0 / PS) ? sc[x0 % PS == NP ? 0 : x0 % PS] : 0.f;
+        const float e1 = (x1 % PS != NP && p == x1 / PS) ? sc[x1 % PS == NP ? 0 : x1 % PS] : 0.f;
+        pk[i] = pack2(e0, e1);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    }
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(region + 16 * piece),
         "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]), "r"(pk[4]), "r"(pk[5]), "r"(pk[6]), "r"(pk[7]), "r"(pk[8]), "r"(pk[9]),
         "r"(pk[10]), "r"(pk[11]), "r"(pk[12]), "r"(pk[13]), "r"(pk[14]), "r"(pk[15]) : "memory");
   }
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void softmax_dispatch(const Ctx& c, int wq, uint32_t region, bool has_mask) {
-  switch (wq) {
-    case 0: softmax_row<0>(c, region, has_mask); break;
-    case 1: softmax_row<1>(c, region, has_mask); break;
-    case 2: softmax_row<2>(c, region, has_mask); break;
-    default: softmax_row<3>(c, region, has_mask); break;
-  }
 }
 
 // element (tall row, k) of tall graph operand `which`
@@ -515,10 +533,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
                        kN16 = idesc_f16(16, false);
     // D[:, dcol..dcol+96) (+)= block a_blk [128 x 96] * W^T
     auto gemm = [&](uint32_t wa, int a_blk, uint32_t dcol, uint32_t accumulate) {
-      const uint32_t a_lo = desc_lo(sbase + OFF_A + a_blk * ABLK_BYTES, A_LBO), b_lo = desc_lo(wa, W_LBO);
-#pragma unroll
-      for (int ks = 0; ks < 6; ++ks)
-        umma_ss(tb + dcol, a_lo + ks * (2 * A_LBO >> 4), kHiK, b_lo + ks * (2 * W_LBO >> 4), kHiK, kN96, (ks > 0) ? 1u : accumulate, leader);
+      uint32_t a_lo = desc_lo(sbase + OFF_A + a_blk * ABLK_BYTES, A_LBO), b_lo = desc_lo(wa, W_LBO), acc = accumulate;
+#pragma unroll 2
+      for (int ks = 0; ks < 6; ++ks) {
+        umma_ss(tb + dcol, a_lo, kHiK, b_lo, kHiK, kN96, acc, leader);
+        a_lo += 2 * A_LBO >> 4; b_lo += 2 * W_LBO >> 4; acc = 1u;
+      }
     };
     auto bias = [&](uint32_t wa, uint32_t dcol) {
       umma_ss(tb + dcol, ones_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
@@ -533,8 +553,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         umma_ss(tb + dcol, a_lo, kHiK, b_lo, kHiActMn, kN96Mn, acc, leader);
         umma_ss(tb + dcol, a_lo + (2 * T_LBO >> 4), kHiK, b_lo + 16, kHiActMn, kN96Mn, 1u, leader);
         acc = 1u;
-        a_lo -= NP;      // window start moves up 17 rows (16 B each, >> 4)
-        b_lo += NP;      // activations of the next pose
+        a_lo -= PS;      // window start moves up one pose (PS rows of 16 B, >> 4)
+        b_lo += PS;      // activations of the next pose
       }
     };
     // S_h[:, 0..128) = Q_h K_h^T; Q = block 0, K = block 1, chunk columns 3h..3h+2 (the 4th one of the second K step is
@@ -658,20 +678,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     float* scratch = reinterpret_cast<float*>(smem + OFF_A);   // [128][16] fp32, aliases the head of operand block 0
     const bool has_mask = a.mask != nullptr;
     uint32_t ps = 0, pphase = 0;                               // parameter stage of the current layer
+    const uint32_t xcol = c.tmem_lane + COL_X + hh * 48;       // this thread's half of its residual row
+    const uint32_t my_chunk = (uint32_t)(OFF_A + a_chunk(row, hh * 6));   // its first chunk inside operand block 0
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
       const int npose = (int)min((long)TP, a.n_rows - g0);
-      const int R = npose * NP;
-      for (int idx = tid; idx < TM * 8; idx += kComputeThreads) {
-        const int r = idx >> 3, cc = idx & 7;
-        float v = 0.f;
-        if (r < R && cc < 5) {
-          const long g = g0 + r / NP;
-          const long src = a.x_is_repeated ? g : (g % a.n_pose);
-          v = a.x_in[(src * NP + (r % NP)) * 5 + cc];
-        }
-        xt[idx] = v;
+      const int nval = npose * NP * 5;                         // valid (pose, joint, coordinate) triples of this tile
+      for (int idx = tid; idx < TM * 8; idx += kComputeThreads) xt[idx] = 0.f;
+      bar_compute();
+      for (int idx = tid; idx < nval; idx += kComputeThreads) {
+        const int p = idx / (NP * 5), rem = idx - p * (NP * 5);
+        const long g = g0 + p;
+        const long src = a.x_is_repeated ? g : (g % a.n_pose);
+        xt[(p * PS + rem / 5) * 8 + rem % 5] = a.x_in[src * (NP * 5) + rem];
       }
       bar_compute();
 
@@ -683,13 +703,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           float pv[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) pv[i] = 0.f;
-          if (r < TR) {
-            const int p = r / NP, i = r - p * NP;
+          const int p = r / PS, i = r - p * PS;
+          if (p < TP && i < NP) {
 #pragma unroll
             for (int cc = 0; cc < 5; ++cc) pv[cc] = xt[r * 8 + cc];
 #pragma unroll
             for (int n = 0; n < NNB; ++n) {
-              const float* u = xt + (p * NP + nbi[i * NNB + n]) * 8;
+              const float* u = xt + (p * PS + nbi[i * NNB + n]) * 8;
               const float2 cf = nbc[i * NNB + n];
 #pragma unroll
               for (int cc = 0; cc < 5; ++cc) { pv[5 + cc] = fmaf(cf.x, u[cc], pv[5 + cc]); pv[10 + cc] = fmaf(cf.y, u[cc], pv[10 + cc]); }
@@ -706,104 +726,79 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         }
         signal_ready(c);                                           // -> 0
         wait_acc(c);
-        float v[48];
-        tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
 
         for (int l = 0; l < L; ++l) {
           // this layer's parameters (LayerNorm gains, L^, temb) have been staged by the producer
           mbar_wait(pfull0 + 8 * ps, pphase);
           const uint8_t* par = smem + OFF_PAR + ps * PAR_BYTES;
           const float* lnp = reinterpret_cast<const float*>(par);
-          const float* temb_s = reinterpret_cast<const float*>(par + LP_BYTES);
           if (tid < 4 * NP) {   // L^ into rows 128..144 of its tall operand
             const int kc = tid / NP, r = tid - kc * NP;
             *reinterpret_cast<uint4*>(smem + OFF_TALL + 2 * TALL_BYTES + kc * T_LBO + (128 + r) * 16) = *reinterpret_cast<const uint4*>(par + LP_LN_BYTES + tid * 16);
           }
+          // The layer is a fixed sequence of compute phases, each followed by "operands ready" and a wait for the
+          // accumulators of the MMA group it feeds (the issuer runs the matching program).  Straight-line code on
+          // purpose: on this part every taken branch to code that is not next in line costs an instruction-cache miss.
+          const uint32_t acol = c.tmem_lane + COL_ACC + hh * 48;    // this thread's half of accumulator group 0
+          uint8_t* const blk0 = smem + my_chunk;                     // its chunks in operand blocks 0, 1, 2
+          uint8_t* const blk1 = blk0 + ABLK_BYTES;
+          uint8_t* const blk2 = blk0 + 2 * ABLK_BYTES;
+          const float ninf = -INFINITY;
           // ======== x = x + attn(LN0(x))
-          layer_norm_rows(c, v, lnp, lnp + H);
-          store_half_row(c, 2, v);
-          signal_ready(c);                                         // -> 1
-          wait_acc(c);
-          // q | k | v: 288 accumulator columns, this thread takes [144*hh, 144*hh+144)
+          ln_run(smem, xcol, row, hh, lnp, lnp + H, my_chunk + 2 * ABLK_BYTES);
+          signal_ready(c); wait_acc(c);                              // -> q, k, v
+          // q | k | v: 288 accumulator columns, this thread takes [144*hh, 144*hh+144) -> blocks 0, 1, 2
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
-            const int col = hh * 144 + g * 48;                     // 0,48,96 | 144,192,240
-            tmem_ld48(c.tmem_lane + COL_ACC + col, v);
-            uint8_t* dst = smem + OFF_A + (col / 96) * ABLK_BYTES;
-            const int kc0 = (col % 96) / 8;
-#pragma unroll
-            for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + a_chunk(row, kc0 + q)) = pack8(v + 8 * q);
+            const int cabs = hh * 144 + g * 48;
+            epi_run(smem + OFF_A + (cabs / 96) * ABLK_BYTES + a_chunk(row, (cabs % 96) / 8), c.tmem_lane + COL_ACC + cabs, ninf, nullptr);
           }
-          signal_ready(c);                                         // -> scores of heads 0, 1
-          wait_acc(c);
-          softmax_dispatch(c, warp & 3, c.tmem_lane + (hh ? COL_S1 : COL_S0), has_mask);
-          signal_ready(c);                                         // -> P V of heads 0, 1; scores of heads 2, 3
-          wait_acc(c);
-          softmax_dispatch(c, warp & 3, c.tmem_lane + (hh ? COL_S1 : COL_S0), has_mask);
-          signal_ready(c);                                         // -> P V of heads 2, 3
-          wait_acc(c);
-          epi_group<0>(c, COL_O, 0, nullptr);
-          signal_ready(c);                                         // -> 2
-          wait_acc(c);
+          signal_ready(c); wait_acc(c);                              // -> scores of heads 0, 1
+          softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
+          signal_ready(c); wait_acc(c);                              // -> P V of heads 0, 1; scores of heads 2, 3
+          softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
+          signal_ready(c); wait_acc(c);                              // -> P V of heads 2, 3
+          epi_run(blk0, c.tmem_lane + COL_O + hh * 48, ninf, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> out projection (accumulates into x)
           // ======== x = x + GraphNet(LN1(x))
-          tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
-          layer_norm_rows(c, v, lnp + 2 * H, lnp + 3 * H);
-          store_half_row(c, 0, v);
-          signal_ready(c);                                         // -> 3
-          wait_acc(c);
-          epi_group<0>(c, COL_ACC, 1, nullptr);
-          signal_ready(c);                                         // -> 4
-          wait_acc(c);
-          epi_group<1>(c, COL_ACC, 0, nullptr);
-          epi_group<1>(c, COL_ACC + 96, 2, nullptr);
-          signal_ready(c);                                         // -> 5
-          wait_acc(c);
-          epi_group<0>(c, COL_ACC, 1, nullptr);
-          signal_ready(c);                                         // -> 6
-          wait_acc(c);
+          ln_run(smem, xcol, row, hh, lnp + 2 * H, lnp + 3 * H, my_chunk);
+          signal_ready(c); wait_acc(c);                              // -> L^ y
+          epi_run(blk1, acol, ninf, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> fc1
+          epi_run(blk0, acol, 0.f, nullptr);
+          epi_run(blk2, acol + 96, 0.f, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> fc2 (+ b2 onto x)
+          epi_run(blk1, acol, ninf, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> L^ z (accumulates into x)
           // ======== x = x + GC2(GC1(x) + temb)
-          tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
-          store_half_row(c, 0, v);
-          signal_ready(c);                                         // -> 7
-          wait_acc(c);
-          epi_group<0>(c, COL_ACC, 1, nullptr);
-          epi_group<0>(c, COL_ACC + 96, 2, nullptr);
-          signal_ready(c);                                         // -> 8
-          wait_acc(c);
-          epi_group<2>(c, COL_ACC, 0, temb_s);
-          // last use of this layer's parameters: hand the stage back to the producer
+          epi_run(blk0, xcol, ninf, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> [T1 x | T2 x]
+          epi_run(blk1, acol, ninf, nullptr);
+          epi_run(blk2, acol + 96, ninf, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> GC1
+          epi_run(blk0, acol, 0.f, reinterpret_cast<const float*>(par + LP_BYTES) + hh * 48);
           __syncwarp();
-          if (lane == 0) mbar_arrive(pempty0 + 8 * ps);
+          if (lane == 0) mbar_arrive(pempty0 + 8 * ps);              // last use of this layer's parameters
+          signal_ready(c); wait_acc(c);                              // -> [T1 h | T2 h]
+          epi_run(blk1, acol, ninf, nullptr);
+          epi_run(blk2, acol + 96, ninf, nullptr);
+          signal_ready(c); wait_acc(c);                              // -> GC2
+          resid_run(xcol, acol);
           if (++ps == 2) { ps = 0; pphase ^= 1; }
-          signal_ready(c);                                         // -> 9
-          wait_acc(c);
-          epi_group<0>(c, COL_ACC, 1, nullptr);
-          epi_group<0>(c, COL_ACC + 96, 2, nullptr);
-          signal_ready(c);                                         // -> 10
-          wait_acc(c);
-          {
-            float u[48];
-            tmem_ld16_async(c.tmem_lane + COL_ACC + hh * 48, u);
-            tmem_ld16_async(c.tmem_lane + COL_ACC + hh * 48 + 16, u + 16);
-            tmem_ld16_async(c.tmem_lane + COL_ACC + hh * 48 + 32, u + 32);
-            tmem_ld48(c.tmem_lane + COL_X + hh * 48, v);
-            launder<48>(u);
-#pragma unroll
-            for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);
-            if (l + 1 < L) tmem_st48(c.tmem_lane + COL_X + hh * 48, v);   // v stays in registers for the next LayerNorm
-          }
         }
 
         // ---- output ChebConv (N = 5): U_k = X Wout_k on the tensor cores with X = hi + lo, then
         //      eps = b + U0 + T1 U1 + T2 U2 and the DDIM update on the CUDA cores
         {
-          uint8_t* d0 = smem + OFF_A;
+          float v[48];
+          tmem_ld48(xcol, v);
+          uint8_t* d0 = smem + my_chunk;
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
             uint4 hi, lo;
             split8(v + 8 * q, hi, lo);
-            *reinterpret_cast<uint4*>(d0 + a_chunk(row, hh * 6 + q)) = hi;
-            *reinterpret_cast<uint4*>(d0 + ABLK_BYTES + a_chunk(row, hh * 6 + q)) = lo;
+            *reinterpret_cast<uint4*>(d0 + q * A_LBO) = hi;
+            *reinterpret_cast<uint4*>(d0 + ABLK_BYTES + q * A_LBO) = lo;
           }
         }
         signal_ready(c);                                           // -> 11
@@ -821,13 +816,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         // eps and the DDIM update (common/utils_diff.py:59-65), same operation order, no FMA contraction
         {
           const dp_step st = a.steps_dev ? a.steps_dev[step] : inl.s[step];
-          for (int idx = tid; idx < R * 5; idx += kComputeThreads) {
-            const int r = idx / 5, n = idx - r * 5;
-            const int p = r / NP, i = r - p * NP;
+          for (int idx = tid; idx < nval; idx += kComputeThreads) {
+            const int p = idx / (NP * 5), rem = idx - p * (NP * 5);
+            const int i = rem / 5, n = rem - i * 5;
+            const int r = p * PS + i;
             float et = __ldg(w.bout + n) + scratch[r * 16 + n];
 #pragma unroll
             for (int q = 0; q < NNB; ++q) {
-              const int rj = p * NP + nbi[i * NNB + q];
+              const int rj = p * PS + nbi[i * NNB + q];
               const float2 cf = nbc[i * NNB + q];
               et = fmaf(cf.x, scratch[rj * 16 + 5 + n], et);
               et = fmaf(cf.y, scratch[rj * 16 + 10 + n], et);
@@ -847,7 +843,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         // aggregation operands, so they must hold finite fp16 again
         if (tid < 4) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
       }
-      for (int idx = tid; idx < R * 5; idx += kComputeThreads) a.out[(size_t)g0 * NP * 5 + idx] = xt[(idx / 5) * 8 + idx % 5];
+      for (int idx = tid; idx < nval; idx += kComputeThreads) {
+        const int p = idx / (NP * 5), rem = idx - p * (NP * 5);
+        a.out[(size_t)g0 * NP * 5 + idx] = xt[(p * PS + rem / 5) * 8 + rem % 5];
+      }
       bar_compute();
     }
   }
