@@ -204,6 +204,7 @@ def main():
     cfg = O.default_config()
     torch.manual_seed(0)
     model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev).set_engine(args.engine)
+    model.eval()     # as the reference's evaluation loop does (runners/diffpose_frame.py:292-293)
     betas = torch.from_numpy(D.get_beta_schedule("linear", beta_start=1e-4, beta_end=1e-3, num_diffusion_timesteps=51)).float()
     steps_arr = D.ddim_steps(betas, seq, eta)
 

@@ -79,6 +79,10 @@ static size_t carve(Weights& w, const Dims& d, float* base) {
   w.bout = c.take(d.c_out);
   w.t1 = c.take(P);
   w.t2 = c.take(P);
+  w.t1m = c.take(P);
+  w.t2m = c.take(P);
+  w.t1s = c.take(d.n_pts);
+  w.t2s = c.take(d.n_pts);
   w.wd0 = c.take((size_t)H * 4 * H);
   w.bd0 = c.take(4 * H);
   w.wd1 = c.take((size_t)16 * H * H);
@@ -111,6 +115,32 @@ static long param_count(const Dims& d) {
 }
 
 static inline float* mut(const float* p) { return const_cast<float*>(p); }
+
+// The Chebyshev matrices of a row-normalised skeleton adjacency have entries such as 1/3 that fp16 cannot hold, and
+// rounding them biases every channel of every pose the same way.  Factor each row i as scale_i * (integers): the
+// integer row is exact in fp16, so the tensor cores apply the matrix exactly and the epilogue multiplies by the fp32
+// scale.  A row without such a factor (arbitrary adjacency) keeps scale 1 and is rounded as before.
+static void integerise_rows(const std::vector<float>& g, int n, std::vector<float>& m, std::vector<float>& scale) {
+  m.assign((size_t)n * n, 0.f);
+  scale.assign(n, 1.f);
+  for (int i = 0; i < n; ++i) {
+    int best = 0;
+    for (int q = 1; q <= 4096 && !best; ++q) {
+      bool ok = true;
+      for (int j = 0; j < n && ok; ++j) {
+        const double v = (double)g[i * n + j] * q, r = std::nearbyint(v);
+        ok = std::fabs(v - r) <= 2e-6 * q && std::fabs(r) <= 2048.0;
+      }
+      if (ok) best = q;
+    }
+    if (best) {
+      scale[i] = 1.0f / (float)best;
+      for (int j = 0; j < n; ++j) m[i * n + j] = (float)std::nearbyint((double)g[i * n + j] * best);
+    } else {
+      for (int j = 0; j < n; ++j) m[i * n + j] = g[i * n + j];
+    }
+  }
+}
 
 static int launch_transpose(float* dst, const float* src, int K, int N, int ld, int col0, cudaStream_t s) {
   int total = K * N;
@@ -190,6 +220,13 @@ static int pack_fp32(dp_model* m, const float* p, const float* adj_host, cudaStr
     }
   DP_CUDA(cudaMemcpyAsync(mut(w.t1), lap.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
   DP_CUDA(cudaMemcpyAsync(mut(w.t2), t2.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
+  std::vector<float> t1m, t1s, t2m, t2s;
+  integerise_rows(lap, NP, t1m, t1s);
+  integerise_rows(t2, NP, t2m, t2s);
+  DP_CUDA(cudaMemcpyAsync(mut(w.t1m), t1m.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
+  DP_CUDA(cudaMemcpyAsync(mut(w.t2m), t2m.data(), P * sizeof(float), cudaMemcpyHostToDevice, s));
+  DP_CUDA(cudaMemcpyAsync(mut(w.t1s), t1s.data(), NP * sizeof(float), cudaMemcpyHostToDevice, s));
+  DP_CUDA(cudaMemcpyAsync(mut(w.t2s), t2s.data(), NP * sizeof(float), cudaMemcpyHostToDevice, s));
   DP_CUDA(cudaMemcpyAsync(m->dw, &m->hw, sizeof(Weights), cudaMemcpyHostToDevice, s));
   // the host vectors above go out of scope: finish the copies first (pack is not on the hot path)
   DP_CUDA(cudaStreamSynchronize(s));
@@ -269,7 +306,7 @@ int dp_set_engine(dp_handle h, int engine) {
 int dp_get_engine(dp_handle h) {
   if (!h) return DP_ERR_INVALID;
   if (h->engine == DP_ENGINE_FP32 || !tc_supported(h->d)) return DP_ENGINE_FP32;
-  return h->engine == DP_ENGINE_TCG ? DP_ENGINE_TCG : DP_ENGINE_TC;
+  return h->engine == DP_ENGINE_TC ? DP_ENGINE_TC : DP_ENGINE_TCG;   // AUTO = the second-generation tensor-core engine
 }
 
 int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char* mask, float* out, long n, void* stream) {

@@ -36,6 +36,8 @@ struct Weights {
   const float *win, *bin;       // [3c_in][hid]
   const float *wout, *bout;     // [3hid][c_out]
   const float *t1, *t2;         // Chebyshev T1 = L, T2 = 2L^2 - I, [n_pts][n_pts]
+  const float *t1m, *t2m;       // the same matrices factored as diag(t?s) * t?m with fp16-exact t?m when the rows allow it
+  const float *t1s, *t2s;       //   (row scales [n_pts]); used by the tensor-core engine, see integerise_rows in dp_api.cu
   const float *wd0, *bd0;       // [hid][4hid]  temb.dense.0
   const float *wd1, *bd1;       // [4hid][4hid] temb.dense.1
   LayerW layer[kMaxLayers];

@@ -60,12 +60,14 @@ constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tr
 constexpr int kComputeThreads = 256;
 constexpr int kProducerWarp = 8, kIssuerWarp = 9;
 constexpr int kThreads = kComputeThreads + 64;
+constexpr int NEV = 4;               // depth of the two hand-over rings ("operands ready", "accumulator ready")
 constexpr int TMEM_COLS = 512;
 constexpr uint32_t COL_X = 0;        // residual stream
 constexpr uint32_t COL_ACC = 96;     // GEMM accumulators (up to 288 columns)
 constexpr uint32_t COL_S0 = 96;      // attention: scores of the even head of a pair [128 x 128]; its probabilities
 constexpr uint32_t COL_S1 = 224;     //   overwrite the first 64 columns as packed fp16 (A operand of P V); odd head
-constexpr uint32_t COL_O = 352;      // attention output [128 x 96] (+8 scratch columns)
+constexpr uint32_t COL_O = 352;      // attention output [128 x 96] (+8 scratch columns); before that the V accumulator
+constexpr uint32_t COL_ACC2 = 288;   // third accumulator group: GEMMs that start while groups 0/1 are still being read
 
 // shared memory map (bytes)
 constexpr int al16(int x) { return (x + 15) / 16 * 16; }
@@ -79,8 +81,8 @@ constexpr int OFF_NBI = OFF_PAR + 2 * PAR_BYTES;           // neighbour index  [
 constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
 constexpr int OFF_STAT = al16(OFF_NBC + NP * NNB * 8);     // LayerNorm partial statistics [2][128] float2
 constexpr int OFF_MASK = OFF_STAT + 2 * TM * 8;            // key mask [32]
-constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], rdy, acc
-constexpr int OFF_TMEM = OFF_BAR + 128;
+constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], rdy[4], acc[4]
+constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_TALL % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
@@ -270,36 +272,43 @@ struct Ctx {
   int trace_n, trace_cap;
   uint8_t* smem;
   uint32_t tmem_lane;   // tmem base + (lane quarter << 16)
-  uint32_t rdy, acc;    // mbarrier addresses
-  uint32_t acc_phase;
+  uint32_t rdy, acc;    // first mbarrier of each ring
+  uint32_t rdy_i, acc_i, acc_phase;   // ring positions (events are produced and consumed in one global program order)
   int row, hh, lane;
 };
 
-__device__ __forceinline__ void trace_mark(Ctx& c) {
-  if (c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = clock64();
+// stamps are (clock64() << 1) | kind, kind 0 = about to signal "operands ready", 1 = "accumulator ready" observed
+__device__ __forceinline__ void trace_mark(Ctx& c, int kind) {
+  if (c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = (clock64() << 1) | kind;
 }
 // "my operands are in shared memory / my TMEM accesses are done": one arrival per compute warp
 __device__ __forceinline__ void signal_ready(Ctx& c) {
-  trace_mark(c);
+  trace_mark(c, 0);
   fence_async_smem();
   tc_fence_before();
   __syncwarp();
-  if (c.lane == 0) mbar_arrive(c.rdy);
+  if (c.lane == 0) mbar_arrive(c.rdy + 8 * c.rdy_i);
+  c.rdy_i = (c.rdy_i + 1) & (NEV - 1);
 }
 __device__ __forceinline__ void wait_acc(Ctx& c) {
-  mbar_wait(c.acc, c.acc_phase);
-  c.acc_phase ^= 1;
+  mbar_wait(c.acc + 8 * c.acc_i, c.acc_phase);
+  c.acc_i = (c.acc_i + 1) & (NEV - 1);
+  if (c.acc_i == 0) c.acc_phase ^= 1;
   tc_fence_after();
-  trace_mark(c);
+  trace_mark(c, 1);
 }
 
 // One epilogue group: 48 accumulator columns of this thread's lane: TMEM -> registers -> clamp (0 = relu, -inf = none)
 // -> (+ temb) -> fp16 -> six 16-byte chunks of an operand block.  Deliberately NOT inlined: the layer body calls it 17
 // times, and one copy of the code keeps the loop inside the instruction cache.  All arguments travel in registers
 // (the shared-memory carve-out leaves next to no L1 for a stack).
-__device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb) {
+__device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false) {
   float v[48];
   tmem_ld48(col, v);
+  if (scaled) {              // row scale of an integerised graph matrix
+#pragma unroll
+    for (int i = 0; i < 48; ++i) v[i] *= scale;
+  }
   if (lo == 0.f) {
 #pragma unroll
     for (int i = 0; i < 48; ++i) v[i] = fmaxf(v[i], 0.f);
@@ -316,9 +325,23 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
 }
 
 // LayerNorm phase: residual row (48 of its 96 channels per thread) from TMEM -> LayerNorm -> fp16 operand block
-__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, int row, int hh, const float* ga, const float* gb, uint32_t dst_off) {
+// With acol != 0 the closing residual of the previous layer's Chebyshev block is applied first: x += relu(acc), written
+// back to TMEM (later MMAs accumulate onto it).
+__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, const float* ga, const float* gb, uint32_t dst_off) {
   float v[48];
-  tmem_ld48(xcol, v);
+  if (acol != 0) {
+    float u[48];
+    tmem_ld16_async(acol, u);
+    tmem_ld16_async(acol + 16, u + 16);
+    tmem_ld16_async(acol + 32, u + 32);
+    tmem_ld48(xcol, v);
+    launder<48>(u);
+#pragma unroll
+    for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);
+    tmem_st48(xcol, v);
+  } else {
+    tmem_ld48(xcol, v);
+  }
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 48; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
@@ -445,16 +468,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   float2* nbc = reinterpret_cast<float2*>(smem + OFF_NBC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   const Weights& w = *a.w;
+  // diagnostic stamps of CTA 0 (last four slots of the trace buffer): kernel entry, setup done, tiles done
+  long long* const ktrace = (blockIdx.x == 0 && tid == 0 && a.trace != nullptr && a.trace_cap >= 8) ? a.trace + a.trace_cap - 4 : nullptr;
+  if (ktrace) ktrace[0] = clock64();
 
   const uint32_t full0 = sbase + OFF_BAR, empty0 = sbase + OFF_BAR + 32, pfull0 = sbase + OFF_BAR + 64, pempty0 = sbase + OFF_BAR + 80,
-                 rdy = sbase + OFF_BAR + 96, accb = sbase + OFF_BAR + 104;
+                 rdy = sbase + OFF_BAR + 96, accb = sbase + OFF_BAR + 128;
 
   // ---------------------------------------------------------------- one-time setup
   if (tid == 0) {
     for (int s = 0; s < NSTAGE; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(pfull0 + 8 * s, 1); mbar_init(pempty0 + 8 * s, kComputeThreads / 32); }
-    mbar_init(rdy, kComputeThreads / 32);
-    mbar_init(accb, 1);
+    for (int s = 0; s < NEV; ++s) { mbar_init(rdy + 8 * s, kComputeThreads / 32); mbar_init(accb + 8 * s, 1); }
     fence_mbar_init();
   }
   __syncwarp();
@@ -466,8 +491,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   for (int i = tid; i < TM; i += kThreads) *reinterpret_cast<uint32_t*>(smem + OFF_ONES + a_chunk(i, 0)) = pack2(1.0f, 1.0f);
   for (int i = tid; i < NP * NP; i += kThreads) {
     const int r = i / NP, k = i - r * NP;
-    *tall_elem(smem, 0, 128 + r, k) = __float2half_rn(__ldg(w.t1 + i));
-    *tall_elem(smem, 1, 128 + r, k) = __float2half_rn(__ldg(w.t2 + i));
+    *tall_elem(smem, 0, 128 + r, k) = __float2half_rn(__ldg(w.t1m + i));     // integer rows, exact in fp16; the row scale
+    *tall_elem(smem, 1, 128 + r, k) = __float2half_rn(__ldg(w.t2m + i));     // is applied by the epilogue
   }
   if (tid < 32) maskf[tid] = (tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f;
   if (tid < NP) {
@@ -484,6 +509,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (ktrace) ktrace[1] = clock64();
 
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int L = a.n_layer;
@@ -518,11 +544,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     // ---------------------------------------------------------------- MMA issuer: the whole warp runs the static program
     // (every value is warp-uniform), one elected lane issues
     const uint32_t leader = elect_one() ? 1u : 0u;
-    uint32_t stage = 0, phase = 0, rdy_phase = 0;
+    uint32_t stage = 0, phase = 0, rdy_i = 0, rdy_phase = 0, acc_i = 0;
     long long* itrace = (blockIdx.x == 0 && a.trace != nullptr && leader) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
     int itrace_n = 0;
     auto imark = [&]() { if (itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
-    auto wait_rdy = [&]() { imark(); mbar_wait(rdy, rdy_phase); rdy_phase ^= 1; tc_fence_after(); imark(); };
+    auto wait_rdy = [&]() {
+      imark();
+      mbar_wait(rdy + 8 * rdy_i, rdy_phase);
+      rdy_i = (rdy_i + 1) & (NEV - 1);
+      if (rdy_i == 0) rdy_phase ^= 1;
+      tc_fence_after();
+      imark();
+    };
+    auto commit_acc = [&]() { umma_commit(accb + 8 * acc_i, leader); acc_i = (acc_i + 1) & (NEV - 1); };
     auto w_acquire = [&]() -> uint32_t { mbar_wait(full0 + 8 * stage, phase); tc_fence_after(); return sbase + OFF_W + stage * WBLK_BYTES; };
     auto w_release = [&]() { umma_commit(empty0 + 8 * stage, leader); if (++stage == NSTAGE) { stage = 0; phase ^= 1; } };
     const uint32_t tb = tmem_base;
@@ -585,65 +619,65 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             umma_ss(tb + COL_X, a_lo + ks * (2 * A_LBO >> 4), kHiK, b_lo + ks * (2 * W_LBO >> 4), kHiK, kN96, ks > 0 ? 1u : 0u, leader);
         }
         w_release();
-        umma_commit(accb, leader);
+        commit_acc();
         for (int l = 0; l < L; ++l) {
-          // 1. q, k, v = LN0(x) W + b                         A = block 2
+          // Every "wait_rdy" consumes the next "operands ready" event of the compute warps, every "commit_acc" produces
+          // the next "accumulator ready" event; both sides walk the same static sequence.  Accumulator groups: ACC+0,
+          // ACC+96 (also the two score regions), ACC2 and the O region, arranged so that a GEMM may start while the
+          // compute warps are still reading the groups of the previous one.
+          // 1. q, k, v = LN0(x) W + b                         A = block 2; one event per output block
           wait_rdy();
-          for (int part = 0; part < 3; ++part) { wa = w_acquire(); gemm(wa, 2, COL_ACC + 96 * part, 0u); bias(wa, COL_ACC + 96 * part); w_release(); }
-          umma_commit(accb, leader);
+          wa = w_acquire(); gemm(wa, 2, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire(); gemm(wa, 2, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
+          wa = w_acquire(); gemm(wa, 2, COL_O, 0u); bias(wa, COL_O); w_release(); commit_acc();
           // 1b. attention, two heads at a time: S = Q_h K_h^T (d_k = 24 = K step of 16 + 8 real | 8 zero columns),
           //     softmax on the compute warps (P back into TMEM), O_h = P V_h with V as an MN-major operand
-          for (int pair = 0; pair < 3; ++pair) {
-            wait_rdy();
-            if (pair > 0)
-              for (int e = 0; e < 2; ++e) pv_head(2 * (pair - 1) + e, e ? COL_S1 : COL_S0);
-            if (pair < 2)
-              for (int e = 0; e < 2; ++e) scores_head(2 * pair + e, e ? COL_S1 : COL_S0);
-            umma_commit(accb, leader);
-          }
+          wait_rdy();                                             // q, k in blocks 0, 1
+          scores_head(0, COL_S0); scores_head(1, COL_S1);
+          commit_acc();
+          wait_rdy();                                             // v in block 2 (its accumulator, the O region, is free)
+          wait_rdy();                                             // P of heads 0, 1
+          pv_head(0, COL_S0); pv_head(1, COL_S1);
+          scores_head(2, COL_S0); scores_head(3, COL_S1);
+          commit_acc();
+          wait_rdy();                                             // P of heads 2, 3
+          pv_head(2, COL_S0); pv_head(3, COL_S1);
+          commit_acc();
           // 2. x += attn Wo + bo                              A = block 0
           wait_rdy();
           wa = w_acquire(); gemm(wa, 0, COL_X, 1u); bias(wa, COL_X); w_release();
-          umma_commit(accb, leader);
+          commit_acc();
           // 3. g1 = L^ LN1(x)                                 B = block 0
           wait_rdy();
           aggregate(2, 0, COL_ACC, 0u);
-          umma_commit(accb, leader);
-          // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1
+          commit_acc();
+          // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1; one event per half
           wait_rdy();
-          for (int part = 0; part < 2; ++part) { wa = w_acquire(); gemm(wa, 1, COL_ACC + 96 * part, 0u); bias(wa, COL_ACC + 96 * part); w_release(); }
-          umma_commit(accb, leader);
-          // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2
+          wa = w_acquire(); gemm(wa, 1, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire(); gemm(wa, 1, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
+          // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2, each as soon as its half of h is there
           wait_rdy();
-          wa = w_acquire(); gemm(wa, 0, COL_ACC, 0u); bias(wa, COL_X); w_release();
-          wa = w_acquire(); gemm(wa, 2, COL_ACC, 1u); w_release();
-          umma_commit(accb, leader);
+          wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_X); w_release();
+          wait_rdy();
+          wa = w_acquire(); gemm(wa, 2, COL_ACC2, 1u); w_release();
+          commit_acc();
           // 6. x += L^ z                                      B = block 1
           wait_rdy();
           aggregate(2, 1, COL_X, 1u);
-          umma_commit(accb, leader);
-          // 7. [T1 x | T2 x]                                  B = block 0
-          wait_rdy();
-          aggregate(0, 0, COL_ACC, 0u);
-          aggregate(1, 0, COL_ACC + 96, 0u);
-          umma_commit(accb, leader);
-          // 8. c1 = [x | T1 x | T2 x] Wc1 + b                 A = blocks 0, 1, 2
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 0, COL_ACC, 0u); bias(wa, COL_ACC); w_release();
-          wa = w_acquire(); gemm(wa, 1, COL_ACC, 1u); w_release();
-          wa = w_acquire(); gemm(wa, 2, COL_ACC, 1u); w_release();
-          umma_commit(accb, leader);
-          // 9. [T1 h1 | T2 h1]                                B = block 0
-          wait_rdy();
-          aggregate(0, 0, COL_ACC, 0u);
-          aggregate(1, 0, COL_ACC + 96, 0u);
-          umma_commit(accb, leader);
-          // 10. c2 = [h1 | T1 h1 | T2 h1] Wc2 + b             A = blocks 0, 1, 2
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 0, COL_ACC, 0u); bias(wa, COL_ACC); w_release();
-          wa = w_acquire(); gemm(wa, 1, COL_ACC, 1u); w_release();
-          wa = w_acquire(); gemm(wa, 2, COL_ACC, 1u); w_release();
-          umma_commit(accb, leader);
+          commit_acc();
+          // 7/8, 9/10. the two Chebyshev convolutions: [T1 v | T2 v] (B = block 0, one event each), and
+          //     [v | T1 v | T2 v] Wc + b into ACC2 -- the v part right away, the others as their operands arrive
+          for (int conv = 0; conv < 2; ++conv) {
+            wait_rdy();
+            aggregate(0, 0, COL_ACC, 0u); commit_acc();
+            aggregate(1, 0, COL_ACC + 96, 0u); commit_acc();
+            wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_ACC2); w_release();
+            wait_rdy();
+            wa = w_acquire(); gemm(wa, 1, COL_ACC2, 1u); w_release();
+            wait_rdy();
+            wa = w_acquire(); gemm(wa, 2, COL_ACC2, 1u); w_release();
+            commit_acc();
+          }
         }
         // 11. U = [X_hi | X_lo | X_hi] [Wout_hi ; Wout_hi ; Wout_lo]   (N = 16: 3 Chebyshev orders x 5 outputs)
         wait_rdy();
@@ -660,7 +694,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           }
         }
         w_release();
-        umma_commit(accb, leader);
+        commit_acc();
       }
     __syncwarp();
   } else {
@@ -671,7 +705,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     c.row = (warp & 3) * 32 + lane;
     c.hh = warp >> 2;
     c.tmem_lane = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
-    c.rdy = rdy; c.acc = accb; c.acc_phase = 0;
+    c.rdy = rdy; c.acc = accb; c.acc_phase = 0; c.rdy_i = 0; c.acc_i = 0;
     c.trace = (blockIdx.x == 0 && tid == 0) ? a.trace : nullptr;
     c.trace_n = 0; c.trace_cap = a.trace_cap / 2;
     const int row = c.row, hh = c.hh;
@@ -680,6 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     uint32_t ps = 0, pphase = 0;                               // parameter stage of the current layer
     const uint32_t xcol = c.tmem_lane + COL_X + hh * 48;       // this thread's half of its residual row
     const uint32_t my_chunk = (uint32_t)(OFF_A + a_chunk(row, hh * 6));   // its first chunk inside operand block 0
+    // row scales of the integerised Chebyshev matrices for this thread's joint (pad rows: anything finite)
+    const float t1scale = __ldg(w.t1s + min(row % PS, NP - 1)), t2scale = __ldg(w.t2s + min(row % PS, NP - 1));
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
@@ -744,54 +780,71 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           uint8_t* const blk1 = blk0 + ABLK_BYTES;
           uint8_t* const blk2 = blk0 + 2 * ABLK_BYTES;
           const float ninf = -INFINITY;
-          // ======== x = x + attn(LN0(x))
-          ln_run(smem, xcol, row, hh, lnp, lnp + H, my_chunk + 2 * ABLK_BYTES);
-          signal_ready(c); wait_acc(c);                              // -> q, k, v
-          // q | k | v: 288 accumulator columns, this thread takes [144*hh, 144*hh+144) -> blocks 0, 1, 2
-#pragma unroll
-          for (int g = 0; g < 3; ++g) {
-            const int cabs = hh * 144 + g * 48;
-            epi_run(smem + OFF_A + (cabs / 96) * ABLK_BYTES + a_chunk(row, (cabs % 96) / 8), c.tmem_lane + COL_ACC + cabs, ninf, nullptr);
-          }
-          signal_ready(c); wait_acc(c);                              // -> scores of heads 0, 1
+          const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48, ocol = c.tmem_lane + COL_O + hh * 48;
+          // ======== x = x + attn(LN0(x))   (first the closing residual of the previous layer's Chebyshev block)
+          ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, lnp, lnp + H, my_chunk + 2 * ABLK_BYTES);
+          signal_ready(c);                                           // LN0(x) in block 2
+          wait_acc(c); epi_run(blk0, acol, ninf, nullptr);           // q
+          wait_acc(c); epi_run(blk1, acol + 96, ninf, nullptr);      // k
+          signal_ready(c);                                           // q, k ready -> scores of heads 0, 1
+          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr);           // v (block 2 = LN0(x) is no longer needed)
+          signal_ready(c);                                           // v ready
+          wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
-          signal_ready(c); wait_acc(c);                              // -> P V of heads 0, 1; scores of heads 2, 3
+          signal_ready(c);                                           // -> P V of heads 0, 1; scores of heads 2, 3
+          wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
-          signal_ready(c); wait_acc(c);                              // -> P V of heads 2, 3
-          epi_run(blk0, c.tmem_lane + COL_O + hh * 48, ninf, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> out projection (accumulates into x)
+          signal_ready(c);                                           // -> P V of heads 2, 3
+          wait_acc(c);
+          epi_run(blk0, ocol, ninf, nullptr);
+          signal_ready(c);                                           // -> out projection (accumulates into x)
+          wait_acc(c);
           // ======== x = x + GraphNet(LN1(x))
-          ln_run(smem, xcol, row, hh, lnp + 2 * H, lnp + 3 * H, my_chunk);
-          signal_ready(c); wait_acc(c);                              // -> L^ y
+          ln_run(smem, xcol, 0u, row, hh, lnp + 2 * H, lnp + 3 * H, my_chunk);
+          signal_ready(c);                                           // -> L^ y
+          wait_acc(c);
           epi_run(blk1, acol, ninf, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> fc1
-          epi_run(blk0, acol, 0.f, nullptr);
-          epi_run(blk2, acol + 96, 0.f, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> fc2 (+ b2 onto x)
-          epi_run(blk1, acol, ninf, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> L^ z (accumulates into x)
+          signal_ready(c);                                           // -> fc1
+          wait_acc(c); epi_run(blk0, acol, 0.f, nullptr);
+          signal_ready(c);                                           // first half of relu(h) -> fc2, first K block
+          wait_acc(c); epi_run(blk2, acol + 96, 0.f, nullptr);
+          signal_ready(c);                                           // second half
+          wait_acc(c);
+          epi_run(blk1, acol2, ninf, nullptr);
+          signal_ready(c);                                           // -> L^ z (accumulates into x)
+          wait_acc(c);
           // ======== x = x + GC2(GC1(x) + temb)
           epi_run(blk0, xcol, ninf, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> [T1 x | T2 x]
-          epi_run(blk1, acol, ninf, nullptr);
-          epi_run(blk2, acol + 96, ninf, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> GC1
-          epi_run(blk0, acol, 0.f, reinterpret_cast<const float*>(par + LP_BYTES) + hh * 48);
+          signal_ready(c);                                           // x as an operand -> [T1 x | T2 x] and x Wc1_0
+          wait_acc(c); epi_run(blk1, acol, ninf, nullptr, t1scale, true);
+          signal_ready(c);                                           // T1 x
+          wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
+          signal_ready(c);                                           // T2 x
+          wait_acc(c);
+          epi_run(blk0, acol2, 0.f, reinterpret_cast<const float*>(par + LP_BYTES) + hh * 48);
           __syncwarp();
           if (lane == 0) mbar_arrive(pempty0 + 8 * ps);              // last use of this layer's parameters
-          signal_ready(c); wait_acc(c);                              // -> [T1 h | T2 h]
-          epi_run(blk1, acol, ninf, nullptr);
-          epi_run(blk2, acol + 96, ninf, nullptr);
-          signal_ready(c); wait_acc(c);                              // -> GC2
-          resid_run(xcol, acol);
+          signal_ready(c);                                           // h = relu(GC1) + temb -> [T1 h | T2 h] and h Wc2_0
+          wait_acc(c); epi_run(blk1, acol, ninf, nullptr, t1scale, true);
+          signal_ready(c);
+          wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
+          signal_ready(c);
+          wait_acc(c);                                               // GC2 in ACC2: the residual is applied by the next phase
           if (++ps == 2) { ps = 0; pphase ^= 1; }
         }
 
         // ---- output ChebConv (N = 5): U_k = X Wout_k on the tensor cores with X = hi + lo, then
         //      eps = b + U0 + T1 U1 + T2 U2 and the DDIM update on the CUDA cores
         {
-          float v[48];
+          float v[48], u[48];
+          const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48;
+          tmem_ld16_async(acol2, u);
+          tmem_ld16_async(acol2 + 16, u + 16);
+          tmem_ld16_async(acol2 + 32, u + 32);
           tmem_ld48(xcol, v);
+          launder<48>(u);
+#pragma unroll
+          for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);   // closing residual of the last layer
           uint8_t* d0 = smem + my_chunk;
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
@@ -850,9 +903,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       bar_compute();
     }
   }
+  if (ktrace) ktrace[2] = clock64();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+  if (ktrace) ktrace[3] = clock64();
 }
 
 // fp32 [K][N] panels of the fp32 blob -> fp16 weight block in the canonical K-major no-swizzle UMMA layout.

@@ -151,6 +151,7 @@ class _FusedBase(nn.Module):
         self._c_in, self._c_out = c_in, c_out
         self._handle = None
         self._packed_version = None
+        self._param_list = None
         self._engine = _lib.ENGINE_AUTO
 
     def _out_dim(self):
@@ -163,6 +164,7 @@ class _FusedBase(nn.Module):
             state_dict = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
         out = super().load_state_dict(state_dict, strict=strict, **kw)
         self._packed_version = None
+        self._param_list = None
         return out
 
     def set_engine(self, engine):
@@ -181,7 +183,34 @@ class _FusedBase(nn.Module):
         return self.gconv_input.weight.device
 
     def _weights_version(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        """Fingerprint that changes whenever the parameters do.  In training mode every parameter is checked (an
+        optimiser step bumps each `_version`); in eval() mode -- the sampling path, where this runs once per batch and a
+        123-tensor walk would cost more host time than the kernel takes -- only the first and last parameter are looked
+        at.  `load_state_dict`, `.to()/.cuda()` and `repack()` invalidate the packed copy explicitly."""
+        if self.training:
+            return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        ps = self._param_list
+        if ps is None:
+            ps = self._param_list = list(self.parameters())
+        a, b = ps[0], ps[-1]
+        return (len(ps), a.data_ptr(), a._version, b.data_ptr(), b._version)
+
+    def repack(self):
+        """Force the device-side packed weights to be rebuilt on the next call (after in-place edits in eval mode)."""
+        self._packed_version = None
+        self._param_list = None
+        return self
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._packed_version = None
+        self._param_list = None
+        return out
+
+    def train(self, mode=True):
+        out = super().train(mode)
+        self._packed_version = None
+        return out
 
     def _ensure_packed(self, device):
         if device.type != "cuda":
@@ -220,6 +249,8 @@ class _FusedBase(nn.Module):
             raise RuntimeError("diffpose_nw_b200 runs on CUDA only (no CPU fallback): got a CPU tensor")
         if x.dim() != 3 or x.shape[1] != self.n_pts or x.shape[2] != c:
             raise RuntimeError(f"expected x of shape [n,{self.n_pts},{c}], got {tuple(x.shape)}")
+        if x.dtype is torch.float32 and x.is_contiguous() and not x.requires_grad:
+            return x
         return x.detach().to(torch.float32).contiguous()
 
     def _forward(self, x, mask, t):

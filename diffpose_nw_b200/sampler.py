@@ -121,12 +121,20 @@ def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_inpu
     if total == 0:
         return out
     mb = m._mask_bytes(src_mask, dev)
-    with torch.cuda.device(dev):
+
+    def launch():
         stream = torch.cuda.current_stream(dev).cuda_stream
-        _lib.check(_lib.load().dp_sample(m._handle, xc.data_ptr(), 0 if repeat_input else 1, out.data_ptr(), n_pose,
-                                         n_hyp, steps, T, nz.data_ptr() if nz is not None else None,
-                                         mb.data_ptr() if mb is not None else None, 1 if mean_over_hyp else 0, stream),
-                   "dp_sample")
+        rc = _lib.load().dp_sample(m._handle, xc.data_ptr(), 0 if repeat_input else 1, out.data_ptr(), n_pose,
+                                   n_hyp, steps, T, nz.data_ptr() if nz is not None else None,
+                                   mb.data_ptr() if mb is not None else None, 1 if mean_over_hyp else 0, stream)
+        if rc != 0:
+            _lib.check(rc, "dp_sample")
+
+    if torch.cuda.current_device() == dev.index:      # the usual case: no device switch on the per-batch path
+        launch()
+    else:
+        with torch.cuda.device(dev):
+            launch()
     return out
 
 

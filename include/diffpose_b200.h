@@ -36,12 +36,14 @@ enum dp_status {
 
 /* Which kernel family executes the denoiser. */
 enum dp_engine {
-  DP_ENGINE_AUTO = 0,  /* tensor-core engine when the configuration allows it, else fp32            */
+  DP_ENGINE_AUTO = 0,  /* DP_ENGINE_TCG when the configuration allows it, else fp32                 */
   DP_ENGINE_FP32 = 1,  /* fp32 FMA persistent kernel: every contraction in fp32 (bit-level reference) */
-  DP_ENGINE_TC = 2,    /* tcgen05 persistent kernel: fp16 operands (11-bit significand, same as TF32),
-                          fp32 accumulation in TMEM; hid_dim=96, n_head=4, n_pts=17 only               */
-  DP_ENGINE_TCG = 3    /* second-generation tcgen05 kernel: residual stream in TMEM, the 17x17 graph
-                          operators on the tensor cores too, dedicated MMA-issuer warp (same limits)     */
+  DP_ENGINE_TC = 2,    /* first tcgen05 persistent kernel, kept for A/B measurements: fp16 operands (11-bit
+                          significand, same as TF32), fp32 accumulation in TMEM, graph operators and attention
+                          on the CUDA cores; hid_dim=96, n_head=4, n_pts=17 only                        */
+  DP_ENGINE_TCG = 3    /* second-generation tcgen05 kernel (the default): every contraction on the tensor cores
+                          (projections, 17x17 graph operators, attention, in/out convolutions), residual stream
+                          in TMEM, dedicated MMA-issuer warp; same limits                                */
 };
 
 /* One DDIM step.  The scalars are evaluated by the caller with the reference's own fp32 tensor ops
@@ -86,7 +88,7 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
 
 /* Select the engine for subsequent dp_forward/dp_sample calls (default DP_ENGINE_AUTO). */
 int dp_set_engine(dp_handle h, int engine);
-/* Engine that a call with the current setting would use (DP_ENGINE_FP32 or DP_ENGINE_TC). */
+/* Engine that a call with the current setting would use (DP_ENGINE_FP32, DP_ENGINE_TC or DP_ENGINE_TCG). */
 int dp_get_engine(dp_handle h);
 
 /* Replaces GCNdiff.forward(x, mask, t, cemd) (models/gcndiff.py:101-113; call sites
@@ -145,8 +147,9 @@ int dp_selftest_umma_ts(const void* smem_image, int image_bytes, const void* tme
 int dp_selftest_cycles(long long* out2);
 
 /* Diagnostic: while dev_buf is set (device pointer, `capacity` 64-bit slots; NULL/0 switches it off), thread 0 of CTA 0 of
- * the DP_ENGINE_TCG kernel stores clock64() at every hand-over between the compute warps and the MMA issuer ("operands
- * ready" just before it is signalled, "accumulator ready" just after it is observed), in program order.  Used by
+ * the DP_ENGINE_TCG kernel stores (clock64() << 1) | kind at every hand-over between the compute warps and the MMA issuer
+ * (kind 0: "operands ready" is about to be signalled, kind 1: "accumulator ready" was observed) in program order in the
+ * first half of the buffer; the issuer stores clock64() before/after each of its waits in the second half.  Used by
  * tools/phase_trace.py to attribute the per-layer time to the individual epilogues and MMA groups. */
 int dp_set_trace(dp_handle h, long long* dev_buf, int capacity);
 

@@ -76,13 +76,14 @@ def gcndiff_forward_tc(sd, adj, n_layer, n_head, x, mask, t):
 
 def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
     """Rounding points of the second-generation tcgen05 engine (csrc/dp_tc2.cu): every tensor-core operand is fp16 --
-    activations, weights and the 17x17 graph matrices (L^, T1, T2), which the kernel applies as per-pose MMAs;
+    activations, weights and the learnable 17x17 matrix L^, which the kernel applies as per-pose MMAs; the Chebyshev
+    matrices T1, T2 are applied exactly (integer rows in fp16 times an fp32 row scale, csrc/dp_api.cu integerise_rows);
     accumulation, the residual stream (TMEM), LayerNorm statistics and softmax are fp32.  Differences from the
     reference order: fc2 is commuted in front of the second L^ aggregation (L^(h W2) + b2), and the Chebyshev input
     panel is [x16 | r16(T1 x16) | r16(T2 x16)].  p16: attention probabilities are fp16 operands too."""
     hid = sd["gconv_input.weight"].shape[-1]
     basis = O.cheb_basis(adj)
-    t1, t2 = r16(basis[1]), r16(basis[2])
+    t1, t2 = basis[1], basis[2]
     temb = O.timestep_embedding(t, hid)
     temb = torch.nn.functional.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
     temb = torch.nn.functional.linear(O.swish(temb), sd["temb.dense.1.weight"], sd["temb.dense.1.bias"])

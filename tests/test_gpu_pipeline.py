@@ -56,7 +56,9 @@ def test_two_stage_pipeline_vs_oracle(engine):
 
 
 def test_shards_equal_whole():
-    """Sharding over ranks never changes a pose's result: the union of 3 contiguous shards equals the unsharded run."""
+    """Sharding over ranks does not change the evaluation: the union of 3 contiguous shards equals the unsharded run
+    (bit-identical on the fp32 engine; on the tensor-core engine a pose's slot in its tile changes the fp32 summation
+    order of P V, so the metric sums agree to ~1e-6 relative)."""
     dev = torch.device("cuda:0")
     adj, diff, sd_d, _, _ = _models()
     diff = diff.to(dev)
@@ -68,4 +70,38 @@ def test_shards_equal_whole():
     for r in range(3):
         lo, hi = D.shard_range(n, r, 3)
         parts += D.evaluate_shard(diff, x[lo:hi].contiguous(), tgt[lo:hi].contiguous(), seq=seq, betas=betas(), test_times=Hh)
+    np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=1e-9 if diff.engine() == "fp32" else 2e-5)
+    diff.set_engine("fp32")
+    whole = D.evaluate_shard(diff, x, tgt, seq=seq, betas=betas(), test_times=Hh)
+    parts = torch.zeros(3, device=dev, dtype=torch.float64)
+    for r in range(3):
+        lo, hi = D.shard_range(n, r, 3)
+        parts += D.evaluate_shard(diff, x[lo:hi].contiguous(), tgt[lo:hi].contiguous(), seq=seq, betas=betas(), test_times=Hh)
     np.testing.assert_allclose(parts.cpu().numpy(), whole.cpu().numpy(), rtol=1e-9)
+
+
+def test_eval_mode_weight_changes_are_picked_up():
+    """eval() mode uses a cheap parameter fingerprint: load_state_dict, .to() and repack() must still invalidate the
+    packed device copy, and training mode must see any in-place edit."""
+    import diffpose_nw_b200 as D
+    from oracle import diffpose_oracle as O
+    from _cases import betas
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config()).to(dev).eval()
+    x = O.synthetic_poses(64, seed=2).to(dev)
+    a = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    sd = O.perturb_state_dict({k: v.detach().cpu().clone() for k, v in model.state_dict().items()}, seed=3)
+    model.load_state_dict(sd)
+    b = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert (a - b).abs().max().item() > 1e-3
+    with torch.no_grad():
+        model.atten_layers[2].self_attn.linears[1].weight.mul_(0.5)      # a middle parameter, edited in place
+    model.repack()
+    c = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert (b - c).abs().max().item() > 1e-5
+    model.train()
+    with torch.no_grad():
+        model.atten_layers[2].self_attn.linears[1].weight.mul_(2.0)
+    d = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert (b - d).abs().max().item() < 1e-5
