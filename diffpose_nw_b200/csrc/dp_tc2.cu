@@ -278,24 +278,27 @@ struct Ctx {
 };
 
 // stamps are (clock64() << 1) | kind, kind 0 = about to signal "operands ready", 1 = "accumulator ready" observed
+template <bool TRACE>
 __device__ __forceinline__ void trace_mark(Ctx& c, int kind) {
-  if (c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = (clock64() << 1) | kind;
+  if (TRACE && c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = (clock64() << 1) | kind;
 }
 // "my operands are in shared memory / my TMEM accesses are done": one arrival per compute warp
-__device__ __forceinline__ void signal_ready(Ctx& c) {
-  trace_mark(c, 0);
+template <bool TRACE>
+__device__ __forceinline__ void signal_ready_t(Ctx& c) {
+  trace_mark<TRACE>(c, 0);
   fence_async_smem();
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(c.rdy + 8 * c.rdy_i);
   c.rdy_i = (c.rdy_i + 1) & (NEV - 1);
 }
-__device__ __forceinline__ void wait_acc(Ctx& c) {
+template <bool TRACE>
+__device__ __forceinline__ void wait_acc_t(Ctx& c) {
   mbar_wait(c.acc + 8 * c.acc_i, c.acc_phase);
   c.acc_i = (c.acc_i + 1) & (NEV - 1);
   if (c.acc_i == 0) c.acc_phase ^= 1;
   tc_fence_after();
-  trace_mark(c, 1);
+  trace_mark<TRACE>(c, 1);
 }
 
 // One epilogue group: 48 accumulator columns of this thread's lane: TMEM -> registers -> clamp (0 = relu, -inf = none)
@@ -458,7 +461,11 @@ __device__ __forceinline__ __half* tall_elem(uint8_t* smem, int which, int trow,
 }
 
 // ------------------------------------------------------------------------------------------------ the kernel
+// TRACE = true compiles the clock64() stamps of dp_set_trace in; the production instantiation carries none of it.
+template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg inl) {
+  auto signal_ready = [](Ctx& c) { signal_ready_t<TRACE>(c); };
+  auto wait_acc = [](Ctx& c) { wait_acc_t<TRACE>(c); };
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t sbase = smem_u32(smem);
@@ -469,7 +476,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   const Weights& w = *a.w;
   // diagnostic stamps of CTA 0 (last four slots of the trace buffer): kernel entry, setup done, tiles done
-  long long* const ktrace = (blockIdx.x == 0 && tid == 0 && a.trace != nullptr && a.trace_cap >= 8) ? a.trace + a.trace_cap - 4 : nullptr;
+  long long* const ktrace = (TRACE && blockIdx.x == 0 && tid == 0 && a.trace != nullptr && a.trace_cap >= 8) ? a.trace + a.trace_cap - 4 : nullptr;
   if (ktrace) ktrace[0] = clock64();
 
   const uint32_t full0 = sbase + OFF_BAR, empty0 = sbase + OFF_BAR + 32, pfull0 = sbase + OFF_BAR + 64, pempty0 = sbase + OFF_BAR + 80,
@@ -545,9 +552,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     // (every value is warp-uniform), one elected lane issues
     const uint32_t leader = elect_one() ? 1u : 0u;
     uint32_t stage = 0, phase = 0, rdy_i = 0, rdy_phase = 0, acc_i = 0;
-    long long* itrace = (blockIdx.x == 0 && a.trace != nullptr && leader) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
+    long long* itrace = (TRACE && blockIdx.x == 0 && a.trace != nullptr && leader) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
     int itrace_n = 0;
-    auto imark = [&]() { if (itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
+    auto imark = [&]() { if (TRACE && itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
     auto wait_rdy = [&]() {
       imark();
       mbar_wait(rdy + 8 * rdy_i, rdy_phase);
@@ -1028,7 +1035,8 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
   if (!m->tc2 || !m->tc2->blocks) { set_error("tensor-core engine: weights are not packed"); return DP_ERR_STATE; }
   static bool configured = false;
   if (!configured) {
-    DP_CUDA(cudaFuncSetAttribute(tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const size_t wbytes = (size_t)m->d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
@@ -1040,7 +1048,8 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
   a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
-  tc2_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);
+  if (a.trace != nullptr) tc2_kernel<true><<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);
+  else tc2_kernel<false><<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);
   count_launch();
   DP_CUDA(cudaGetLastError());
   m->last_launch[0] = grid; m->last_launch[1] = kThreads; m->last_launch[2] = SMEM_BYTES;
