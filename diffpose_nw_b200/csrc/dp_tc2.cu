@@ -474,7 +474,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   int* nbi = reinterpret_cast<int*>(smem + OFF_NBI);
   float2* nbc = reinterpret_cast<float2*>(smem + OFF_NBC);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
-  const Weights& w = *a.w;
   // diagnostic stamps of CTA 0 (last four slots of the trace buffer): kernel entry, setup done, tiles done
   long long* const ktrace = (TRACE && blockIdx.x == 0 && tid == 0 && a.trace != nullptr && a.trace_cap >= 8) ? a.trace + a.trace_cap - 4 : nullptr;
   if (ktrace) ktrace[0] = clock64();
@@ -496,6 +495,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   __syncthreads();
   // constant-one K slab: element (row, 0) = (row, 1) = 1
   for (int i = tid; i < TM; i += kThreads) *reinterpret_cast<uint32_t*>(smem + OFF_ONES + a_chunk(i, 0)) = pack2(1.0f, 1.0f);
+  // Programmatic dependent launch: this grid may have started while the previous kernel of the stream was still
+  // draining.  Nothing above touches global memory; wait here for the previous kernel's results (x_in may be its
+  // output, the temb table and the packed weights are written by earlier kernels of the same stream).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const Weights& w = *a.w;
   for (int i = tid; i < NP * NP; i += kThreads) {
     const int r = i / NP, k = i - r * NP;
     *tall_elem(smem, 0, 128 + r, k) = __float2half_rn(__ldg(w.t1m + i));     // integer rows, exact in fp16; the row scale
@@ -517,6 +521,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (ktrace) ktrace[1] = clock64();
+  // let the next kernel of the stream begin its launch: its CTAs take over each SM as ours retire
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int L = a.n_layer;
@@ -1048,8 +1054,14 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
   a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
-  if (a.trace != nullptr) tc2_kernel<true><<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);
-  else tc2_kernel<false><<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (a.trace != nullptr) DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<true>, a, *inl));
+  else DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<false>, a, *inl));
   count_launch();
   DP_CUDA(cudaGetLastError());
   m->last_launch[0] = grid; m->last_launch[1] = kThreads; m->last_launch[2] = SMEM_BYTES;
