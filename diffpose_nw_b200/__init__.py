@@ -11,8 +11,8 @@ from .graph import H36M_EDGES, adj_mx_from_edges
 from .model import FusedGCNdiff, FusedGCNpose
 from .sampler import compute_alpha, ddim_steps, generalized_steps, get_beta_schedule, make_seq, sample
 from .metrics import mpjpe, p_mpjpe, pose_error_sums
-from .pipeline import evaluate_shard, lift_and_refine, reduce_metrics, shard_range
+from .pipeline import HostStream, evaluate_shard, lift_and_refine, reduce_metrics, shard_range
 
 __all__ = ["H36M_EDGES", "adj_mx_from_edges", "FusedGCNdiff", "FusedGCNpose", "compute_alpha", "ddim_steps",
            "generalized_steps", "get_beta_schedule", "make_seq", "sample", "mpjpe", "p_mpjpe", "pose_error_sums",
-           "evaluate_shard", "lift_and_refine", "reduce_metrics", "shard_range"]
+           "HostStream", "evaluate_shard", "lift_and_refine", "reduce_metrics", "shard_range"]

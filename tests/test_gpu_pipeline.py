@@ -105,3 +105,25 @@ def test_eval_mode_weight_changes_are_picked_up():
         model.atten_layers[2].self_attn.linears[1].weight.mul_(2.0)
     d = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
     assert (b - d).abs().max().item() < 1e-5
+
+
+def test_host_stream_matches_direct_calls():
+    """HostStream (overlapped H2D / kernel / D2H ring) returns, in order, exactly what one-at-a-time calls return."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config()).to(dev).eval()
+    seq = [0, 12]
+    batches = [O.synthetic_poses(n, seed=60 + i).pin_memory() for i, n in enumerate([64, 64, 10, 64, 33, 64, 64])]
+    want = [D.generalized_steps(b.to(dev), None, seq, model, betas())[0][-1].cpu() for b in batches]
+    hs = D.HostStream(model, batch=64, seq=seq, betas=betas(), depth=3)
+    got = []
+    for b in batches:
+        r = hs.submit(b)
+        if r is not None:
+            got.append(r.clone())
+    got += [t.clone() for t in hs.drain()]
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert g.shape == w.shape and torch.equal(g, w)
+    with pytest.raises(RuntimeError, match="exceeds"):
+        hs.submit(O.synthetic_poses(65).pin_memory())
