@@ -83,3 +83,25 @@ def test_tc_matches_fp32_engine_on_many_tiles(engine):
     b = D.generalized_steps(x, None, [0, 12], model.set_engine(engine), betas())[0][-1]
     assert (a - b).abs().max().item() < 1e-3
     assert torch.equal(b, D.generalized_steps(x, None, [0, 12], model, betas())[0][-1])
+
+
+def test_tcg_repeatable_across_ring_wraps():
+    """Race hunting without a sanitizer: several tiles per CTA (every mbarrier ring wraps many times), three steps, noise and
+    a key mask; 12 repetitions must be bit-identical and match the fp32 engine within the operand-precision tolerance."""
+    cfg = O.default_config()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev()).eval()
+    n, Hh, seq = 3100, 2, [0, 6, 12]
+    x = O.synthetic_poses(n, seed=21).to(dev())
+    g = torch.Generator().manual_seed(22)
+    noise = torch.randn(len(seq), Hh * n, 17, 5, generator=g).to(dev())
+    mask = torch.ones(1, 1, 17, dtype=torch.bool, device=dev())
+    mask[0, 0, 3] = False
+    mask[0, 0, 11] = False
+    run = lambda: D.sample(model, x, mask, seq, betas(), eta=1.0, noise=noise, n_hyp=Hh, repeat_input=True)
+    first = run()
+    assert torch.isfinite(first).all()
+    for _ in range(11):
+        assert torch.equal(run(), first)
+    ref = D.sample(model.set_engine("fp32"), x, mask, seq, betas(), eta=1.0, noise=noise, n_hyp=Hh, repeat_input=True)
+    assert (first - ref).abs().max().item() < 1e-3
