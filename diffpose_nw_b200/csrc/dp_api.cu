@@ -286,7 +286,8 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   DP_TRY(pack_fp32(h, params, adj_host, s));
-  if (tc_supported(h->d)) { DP_TRY(tc_pack(h, s)); DP_TRY(tc2_pack(h, s)); }
+  if (tc_supported(h->d)) DP_TRY(tc_pack(h, s));
+  if (tc2_supported(h->d)) DP_TRY(tc2_pack(h, s));
   h->temb_t.clear();
   h->packed = true;
   return DP_OK;
@@ -295,8 +296,8 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
 int dp_set_engine(dp_handle h, int engine) {
   DP_REQUIRE(h, "dp_set_engine: NULL handle");
   DP_REQUIRE(engine == DP_ENGINE_AUTO || engine == DP_ENGINE_FP32 || engine == DP_ENGINE_TC || engine == DP_ENGINE_TCG, "dp_set_engine: unknown engine");
-  if ((engine == DP_ENGINE_TC || engine == DP_ENGINE_TCG) && !tc_supported(h->d)) {
-    set_error("dp_set_engine: the tensor-core engine needs hid_dim=96, n_head=4, n_pts=17");
+  if ((engine == DP_ENGINE_TC && !tc_supported(h->d)) || (engine == DP_ENGINE_TCG && !tc2_supported(h->d))) {
+    set_error("dp_set_engine: the tensor-core engines need hid_dim=96, n_head=4, n_pts=17 (the first one also uvxyz in and out)");
     return DP_ERR_UNSUPPORTED;
   }
   h->engine = engine;
@@ -305,8 +306,9 @@ int dp_set_engine(dp_handle h, int engine) {
 
 int dp_get_engine(dp_handle h) {
   if (!h) return DP_ERR_INVALID;
-  if (h->engine == DP_ENGINE_FP32 || !tc_supported(h->d)) return DP_ENGINE_FP32;
-  return h->engine == DP_ENGINE_TC ? DP_ENGINE_TC : DP_ENGINE_TCG;   // AUTO = the second-generation tensor-core engine
+  if (h->engine == DP_ENGINE_FP32 || !tc2_supported(h->d)) return DP_ENGINE_FP32;
+  if (h->engine == DP_ENGINE_TC) return tc_supported(h->d) ? DP_ENGINE_TC : DP_ENGINE_TCG;
+  return DP_ENGINE_TCG;   // AUTO = the second-generation tensor-core engine
 }
 
 int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char* mask, float* out, long n, void* stream) {
@@ -316,8 +318,10 @@ int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char*
   DP_REQUIRE(!h->d.has_temb || t != nullptr, "dp_forward: t is required for the diffusion denoiser");
   if (n == 0) return DP_OK;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
-  // Per-sample timesteps need a per-sample embedding table; the fp32 engine serves this entry point.
-  h->temb_t.clear();   // the table buffer is about to be reused for per-sample rows
+  // Per-sample timesteps need a per-sample embedding table (computed in chunks into the same buffer the sampler caches
+  // its per-step table in, so that cache is dropped).  The first tensor-core engine has no forward entry: it falls to fp32.
+  h->temb_t.clear();
+  if (dp_get_engine(h) == DP_ENGINE_TCG) return tc2_forward(h, x, t, mask, out, n, s);
   return simt_forward(h, x, t, mask, out, n, s);
 }
 

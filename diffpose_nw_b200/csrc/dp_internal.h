@@ -130,6 +130,8 @@ int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, in
            const void* tmem_image_dev, int tmem_col0, int tmem_ncols, cudaStream_t s);
 void tc_lab_cycles(long long* out2);
 // dp_tc2.cu
+bool tc2_supported(const Dims& d);
+int tc2_forward(dp_model* m, const float* x, const float* t, const unsigned char* mask, float* out, long n, cudaStream_t s);
 int tc2_pack(dp_model* m, cudaStream_t s);
 void tc2_free(dp_model* m);
 int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,

@@ -77,7 +77,8 @@ constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
 constexpr int OFF_W = (OFF_TALL + 3 * TALL_BYTES + 127) / 128 * 128;
 constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][8] fp32
 constexpr int OFF_PAR = OFF_XT + TM * 8 * 4;               // per-layer parameters, 2 stages
-constexpr int OFF_NBI = OFF_PAR + 2 * PAR_BYTES;           // neighbour index  [17][9] int
+constexpr int OFF_TEP = OFF_PAR + 2 * PAR_BYTES;           // per-pose temb [7][96] fp32 (forward mode: per-sample timesteps)
+constexpr int OFF_NBI = OFF_TEP + TP * H * 4;              // neighbour index  [17][9] int
 constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
 constexpr int OFF_STAT = al16(OFF_NBC + NP * NNB * 8);     // LayerNorm partial statistics [2][128] float2
 constexpr int OFF_MASK = OFF_STAT + 2 * TM * 8;            // key mask [32]
@@ -253,12 +254,15 @@ struct Tc2Args {
   const uint8_t* ioblocks;   // [2][21504 B]: input-convolution block, output-convolution block
   const uint8_t* lparams;    // [n_layer][LP_BYTES]
   int n_layer;
+  int c_in, c_out;           // coordinate widths (<= 5): uvxyz -> uvxyz for GCNdiff, uv -> xyz for GCNpose
+  int forward_only;          // 1: a single denoiser/lifter forward, the output is eps (dp_forward); 0: the DDIM loop
+  int has_temb;              // GCNpose has no time embedding
   const float* x_in;
   int x_is_repeated;
   float* out;
   long n_rows, n_pose;
   int n_steps;
-  const float* temb;         // [n_steps][n_layer][96]
+  const float* temb;         // [n_steps][n_layer][96], or [n_rows][n_layer][96] (per-sample timesteps) when forward_only
   const float* noise;
   const unsigned char* mask;
   const dp_step* steps_dev;
@@ -543,9 +547,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           put_block(a.ioblocks);
           for (int l = 0; l < L; ++l) {
             mbar_wait_sleep(pempty0 + 8 * ps, pphase ^ 1);
-            mbar_expect_tx(pfull0 + 8 * ps, PAR_BYTES);
+            const bool step_temb = !a.forward_only && a.has_temb;     // one temb row per (step, layer), shared by the batch
+            mbar_expect_tx(pfull0 + 8 * ps, step_temb ? PAR_BYTES : LP_BYTES);
             bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES, a.lparams + (size_t)l * LP_BYTES, LP_BYTES, pfull0 + 8 * ps);
-            bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES + LP_BYTES, a.temb + ((size_t)step * L + l) * H, H * 4, pfull0 + 8 * ps);
+            if (step_temb) bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES + LP_BYTES, a.temb + ((size_t)step * L + l) * H, H * 4, pfull0 + 8 * ps);
             if (++ps == 2) { ps = 0; pphase ^= 1; }
             for (int blk = 0; blk < BLOCKS_PER_LAYER; ++blk) put_block(a.wpack + ((size_t)l * BLOCKS_PER_LAYER + blk) * WBLK_BYTES);
           }
@@ -733,14 +738,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
       const int npose = (int)min((long)TP, a.n_rows - g0);
-      const int nval = npose * NP * 5;                         // valid (pose, joint, coordinate) triples of this tile
+      const int ci = a.c_in, co = a.c_out;
+      const int nin = npose * NP * ci, nval = npose * NP * co;  // valid (pose, joint, coordinate) triples: input, output
       for (int idx = tid; idx < TM * 8; idx += kComputeThreads) xt[idx] = 0.f;
       bar_compute();
-      for (int idx = tid; idx < nval; idx += kComputeThreads) {
-        const int p = idx / (NP * 5), rem = idx - p * (NP * 5);
+      for (int idx = tid; idx < nin; idx += kComputeThreads) {
+        const int p = idx / (NP * ci), rem = idx - p * (NP * ci);
         const long g = g0 + p;
         const long src = a.x_is_repeated ? g : (g % a.n_pose);
-        xt[(p * PS + rem / 5) * 8 + rem % 5] = a.x_in[src * (NP * 5) + rem];
+        xt[(p * PS + rem / ci) * 8 + rem % ci] = a.x_in[src * (NP * ci) + rem];
       }
       bar_compute();
 
@@ -781,6 +787,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           mbar_wait(pfull0 + 8 * ps, pphase);
           const uint8_t* par = smem + OFF_PAR + ps * PAR_BYTES;
           const float* lnp = reinterpret_cast<const float*>(par);
+          if (a.forward_only && a.has_temb && tid < TP * (H / 4)) {   // per-sample timesteps: this layer's temb row of every pose
+            const int p = tid / (H / 4), c4 = tid - p * (H / 4);
+            float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p < npose) tv = __ldg(reinterpret_cast<const float4*>(a.temb + ((size_t)(g0 + p) * L + l) * H) + c4);
+            reinterpret_cast<float4*>(smem + OFF_TEP)[tid] = tv;
+          }
           if (tid < 4 * NP) {   // L^ into rows 128..144 of its tall operand
             const int kc = tid / NP, r = tid - kc * NP;
             *reinterpret_cast<uint4*>(smem + OFF_TALL + 2 * TALL_BYTES + kc * T_LBO + (128 + r) * 16) = *reinterpret_cast<const uint4*>(par + LP_LN_BYTES + tid * 16);
@@ -794,6 +806,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           uint8_t* const blk2 = blk0 + 2 * ABLK_BYTES;
           const float ninf = -INFINITY;
           const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48, ocol = c.tmem_lane + COL_O + hh * 48;
+          // temb added after GC1 (gcndiff.py:51): one row per (step, layer) in the sampler, one per pose in a forward call,
+          // none for GCNpose
+          const float* temb_row = !a.has_temb ? nullptr
+                                  : (a.forward_only ? reinterpret_cast<const float*>(smem + OFF_TEP) + min(row / PS, TP - 1) * H
+                                                    : reinterpret_cast<const float*>(par + LP_BYTES)) + hh * 48;
           // ======== x = x + attn(LN0(x))   (first the closing residual of the previous layer's Chebyshev block)
           ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, lnp, lnp + H, my_chunk + 2 * ABLK_BYTES);
           signal_ready(c);                                           // LN0(x) in block 2
@@ -834,7 +851,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
           signal_ready(c);                                           // T2 x
           wait_acc(c);
-          epi_run(blk0, acol2, 0.f, reinterpret_cast<const float*>(par + LP_BYTES) + hh * 48);
+          epi_run(blk0, acol2, 0.f, temb_row);
           __syncwarp();
           if (lane == 0) mbar_arrive(pempty0 + 8 * ps);              // last use of this layer's parameters
           signal_ready(c);                                           // h = relu(GC1) + temb -> [T1 h | T2 h] and h Wc2_0
@@ -879,12 +896,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         }
         tc_fence_before();
         bar_compute();
-        // eps and the DDIM update (common/utils_diff.py:59-65), same operation order, no FMA contraction
+        // eps = b + U0 + T1 U1 + T2 U2, then either the DDIM update (common/utils_diff.py:59-65, same operation order, no FMA
+        // contraction) or, for a plain forward call, the store of eps
         {
           const dp_step st = a.steps_dev ? a.steps_dev[step] : inl.s[step];
           for (int idx = tid; idx < nval; idx += kComputeThreads) {
-            const int p = idx / (NP * 5), rem = idx - p * (NP * 5);
-            const int i = rem / 5, n = rem - i * 5;
+            const int p = idx / (NP * co), rem = idx - p * (NP * co);
+            const int i = rem / co, n = rem - i * co;
             const int r = p * PS + i;
             float et = __ldg(w.bout + n) + scratch[r * 16 + n];
 #pragma unroll
@@ -894,11 +912,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
               et = fmaf(cf.x, scratch[rj * 16 + 5 + n], et);
               et = fmaf(cf.y, scratch[rj * 16 + 10 + n], et);
             }
+            if (a.forward_only) {
+              a.out[(size_t)g0 * NP * co + idx] = et;
+              continue;
+            }
             const float xv = xt[r * 8 + n];
             const float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(et, st.sqrt_1m_at)), st.sqrt_at);
             float nx = __fmul_rn(st.sqrt_an, x0);
             if (a.noise) {
-              const float z = a.noise[((size_t)step * a.n_rows + g0) * NP * 5 + idx];
+              const float z = a.noise[((size_t)step * a.n_rows + g0) * NP * co + idx];
               nx = __fadd_rn(nx, __fmul_rn(st.c1, z));
             }
             xt[r * 8 + n] = __fadd_rn(nx, __fmul_rn(st.c2, et));
@@ -909,9 +931,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         // aggregation operands, so they must hold finite fp16 again
         if (tid < 4) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
       }
-      for (int idx = tid; idx < nval; idx += kComputeThreads) {
-        const int p = idx / (NP * 5), rem = idx - p * (NP * 5);
-        a.out[(size_t)g0 * NP * 5 + idx] = xt[(p * PS + rem / 5) * 8 + rem % 5];
+      if (!a.forward_only) {
+        for (int idx = tid; idx < nval; idx += kComputeThreads) {
+          const int p = idx / (NP * co), rem = idx - p * (NP * co);
+          a.out[(size_t)g0 * NP * co + idx] = xt[(p * PS + rem / co) * 8 + rem % co];
+        }
       }
       bar_compute();
     }
@@ -940,15 +964,19 @@ __global__ void tc2_pack_block_kernel(uint8_t* __restrict__ dst, const float* __
 
 __device__ __forceinline__ float hi16(float v) { return __half2float(__float2half_rn(v)); }
 
-// Input convolution block [N=96][K=48]: K slabs [hi ; hi ; lo] of the panel weights Win [15][96] with the bias in row 15.
+// Input convolution block [N=96][K=48]: K slabs [hi ; hi ; lo] of the panel weights Win [3*c_in][96]; panel position
+// k = order*5 + coordinate (coordinates >= c_in are zero), the bias sits in row 15.
 // Output convolution block [N=16][K=288] (K-adjacent core matrices OUT_LBO apart): slabs [hi ; hi ; lo] of Wout
-// reshaped to [96][3*5] (column = order*5 + output), column 15 zero.  Both blocks are zero padded to WBLK_BYTES.
+// [3][96][c_out] reshaped to columns order*5 + output (outputs >= c_out and column 15 are zero).  Both blocks are zero
+// padded to WBLK_BYTES.
 __global__ void tc2_pack_io_kernel(uint8_t* __restrict__ dst, const float* __restrict__ win, const float* __restrict__ bin,
-                                   const float* __restrict__ wout) {
+                                   const float* __restrict__ wout, int c_in, int c_out) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 96 * 48; idx += gridDim.x * blockDim.x) {
     const int n = idx / 48, k = idx - n * 48;
     const int slab = k >> 4, kk = k & 15;
-    const float full = kk < 15 ? win[kk * 96 + n] : bin[n];
+    float full = 0.f;
+    if (kk == 15) full = bin[n];
+    else if (kk % 5 < c_in) full = win[((kk / 5) * c_in + kk % 5) * 96 + n];
     const float v = slab < 2 ? hi16(full) : full - hi16(full);
     const size_t off = (size_t)(k >> 3) * W_LBO + (size_t)(n >> 3) * W_SBO + (n & 7) * 16 + (k & 7) * 2;
     *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
@@ -958,7 +986,7 @@ __global__ void tc2_pack_io_kernel(uint8_t* __restrict__ dst, const float* __res
     const int n = idx / 288, k = idx - n * 288;
     const int slab = k / 96, ch = k - slab * 96;
     float full = 0.f;
-    if (n < 15) full = wout[((n / 5) * 96 + ch) * 5 + (n % 5)];
+    if (n < 15 && n % 5 < c_out) full = wout[((n / 5) * 96 + ch) * c_out + (n % 5)];
     const float v = slab < 2 ? hi16(full) : full - hi16(full);
     const size_t off = (size_t)(k >> 3) * OUT_LBO + (size_t)(n >> 3) * 128 + (n & 7) * 16 + (k & 7) * 2;
     *reinterpret_cast<__half*>(d2 + off) = __float2half_rn(v);
@@ -1029,15 +1057,17 @@ int tc2_pack(dp_model* m, cudaStream_t s) {
     count_launch();
     DP_CUDA(cudaGetLastError());
   }
-  tc2_pack_io_kernel<<<18, 256, 0, s>>>(m->tc2->blocks + wbytes, m->hw.win, m->hw.bin, m->hw.wout);
+  tc2_pack_io_kernel<<<18, 256, 0, s>>>(m->tc2->blocks + wbytes, m->hw.win, m->hw.bin, m->hw.wout, d.c_in, d.c_out);
   count_launch();
   DP_CUDA(cudaGetLastError());
   return DP_OK;
 }
 
-int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
-               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
-               const unsigned char* mask, cudaStream_t s) {
+bool tc2_supported(const Dims& d) {
+  return d.hid == 96 && d.n_head == 4 && d.n_pts == 17 && d.c_in >= 1 && d.c_in <= 5 && d.c_out >= 1 && d.c_out <= 5;
+}
+
+static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t s) {
   if (!m->tc2 || !m->tc2->blocks) { set_error("tensor-core engine: weights are not packed"); return DP_ERR_STATE; }
   static bool configured = false;
   if (!configured) {
@@ -1046,11 +1076,9 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
     configured = true;
   }
   const size_t wbytes = (size_t)m->d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
-  Tc2Args a{};
   a.w = m->dw; a.wpack = m->tc2->blocks; a.ioblocks = m->tc2->blocks + wbytes; a.lparams = m->tc2->blocks + wbytes + 2 * WBLK_BYTES;
-  a.n_layer = m->d.n_layer; a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
-  a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_steps = n_steps; a.temb = m->temb; a.noise = noise; a.mask = mask;
-  a.steps_dev = steps_dev;
+  a.n_layer = m->d.n_layer; a.c_in = m->d.c_in; a.c_out = m->d.c_out; a.has_temb = m->d.has_temb;
+  a.temb = m->temb;
   a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
@@ -1063,9 +1091,34 @@ int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, 
   if (a.trace != nullptr) DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<true>, a, *inl));
   else DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<false>, a, *inl));
   count_launch();
-  DP_CUDA(cudaGetLastError());
   m->last_launch[0] = grid; m->last_launch[1] = kThreads; m->last_launch[2] = SMEM_BYTES;
   m->last_launch[3] = TP; m->last_launch[4] = DP_ENGINE_TCG; m->last_launch[5] = n_tiles;
+  return DP_OK;
+}
+
+int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
+               const unsigned char* mask, cudaStream_t s) {
+  Tc2Args a{};
+  a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
+  a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_steps = n_steps; a.noise = noise; a.mask = mask;
+  a.steps_dev = steps_dev; a.forward_only = 0;
+  return tc2_launch(m, a, inl, s);
+}
+
+// GCNdiff.forward / GCNpose.forward (models/gcndiff.py:101-113, models/gcnpose.py:101-113): one pass, per-sample timesteps
+int tc2_forward(dp_model* m, const float* x, const float* t, const unsigned char* mask, float* out, long n, cudaStream_t s) {
+  const Dims& d = m->d;
+  const long chunk = 1L << 16;  // bounds the per-sample embedding table (chunk * n_layer * hid floats)
+  StepsArg none{};
+  for (long o = 0; o < n; o += chunk) {
+    const long nn = (n - o < chunk) ? (n - o) : chunk;
+    if (d.has_temb) DP_TRY(simt_temb(m, t + o, 1, nullptr, nn, s));
+    Tc2Args a{};
+    a.x_in = x + (size_t)o * d.n_pts * d.c_in; a.x_is_repeated = 1; a.out = out + (size_t)o * d.n_pts * d.c_out;
+    a.n_rows = nn; a.n_pose = nn; a.n_steps = 1; a.noise = nullptr; a.mask = mask; a.steps_dev = nullptr; a.forward_only = 1;
+    DP_TRY(tc2_launch(m, a, &none, s));
+  }
   return DP_OK;
 }
 

@@ -74,6 +74,11 @@ def gcndiff_forward_tc(sd, adj, n_layer, n_head, x, mask, t):
     return O.cheb_conv(X, adj, sd["gconv_output.weight"], sd["gconv_output.bias"])
 
 
+def gcnpose_forward_tcg(sd, adj, n_layer, n_head, x, mask, p16=True):
+    """GCNpose (models/gcnpose.py:101-113) on the second-generation engine: the same rounding points, no time embedding."""
+    return gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, None, p16=p16)
+
+
 def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
     """Rounding points of the second-generation tcgen05 engine (csrc/dp_tc2.cu): every tensor-core operand is fp16 --
     activations, weights and the learnable 17x17 matrix L^, which the kernel applies as per-pose MMAs; the Chebyshev
@@ -84,15 +89,17 @@ def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
     hid = sd["gconv_input.weight"].shape[-1]
     basis = O.cheb_basis(adj)
     t1, t2 = basis[1], basis[2]
-    temb = O.timestep_embedding(t, hid)
-    temb = torch.nn.functional.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
-    temb = torch.nn.functional.linear(O.swish(temb), sd["temb.dense.1.weight"], sd["temb.dense.1.bias"])
+    temb = None
+    if t is not None:     # GCNpose (t = None) has no time embedding
+        temb = O.timestep_embedding(t, hid)
+        temb = torch.nn.functional.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
+        temb = torch.nn.functional.linear(O.swish(temb), sd["temb.dense.1.weight"], sd["temb.dense.1.bias"])
 
     def cheb_tc(v16, w, b):
         a = torch.cat([v16, r16(torch.matmul(t1, v16)), r16(torch.matmul(t2, v16))], dim=-1)
         return a @ r16(w.reshape(3 * w.shape[2], w.shape[3])) + split16(b.reshape(-1))
 
-    X = O.cheb_conv(x, adj, sd["gconv_input.weight"], sd["gconv_input.bias"])      # K = 15: fp32 on CUDA cores
+    X = O.cheb_conv(x, adj, sd["gconv_input.weight"], sd["gconv_input.bias"])      # hi/lo split MMAs: fp32-level accuracy
     d_k = hid // n_head
     for l in range(n_layer):
         p, g = f"atten_layers.{l}", f"gconv_layers.{l}"
@@ -119,7 +126,8 @@ def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
         X = X + torch.matmul(lhat, z) + split16(sd[f"{p}.feed_forward.gconv2.fc.bias"])
         # residual Chebyshev block
         h1 = torch.relu(cheb_tc(r16(X), sd[f"{g}.gconv1.gconv.weight"], sd[f"{g}.gconv1.gconv.bias"]))
-        h1 = h1 + torch.nn.functional.linear(O.swish(temb), sd[f"{g}.temb_proj.weight"], sd[f"{g}.temb_proj.bias"])[:, None, :]
+        if temb is not None:
+            h1 = h1 + torch.nn.functional.linear(O.swish(temb), sd[f"{g}.temb_proj.weight"], sd[f"{g}.temb_proj.bias"])[:, None, :]
         h2 = torch.relu(cheb_tc(r16(h1), sd[f"{g}.gconv2.gconv.weight"], sd[f"{g}.gconv2.gconv.bias"]))
         X = X + h2
     return O.cheb_conv(X, adj, sd["gconv_output.weight"], sd["gconv_output.bias"])

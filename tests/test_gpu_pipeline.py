@@ -30,7 +30,7 @@ def _models():
 def test_two_stage_pipeline_vs_oracle(engine):
     dev = torch.device("cuda:0")
     adj, diff, sd_d, pose, sd_p = _models()
-    diff, pose = diff.to(dev).set_engine(engine), pose.to(dev)
+    diff, pose = diff.to(dev).set_engine(engine), pose.to(dev).set_engine(engine)
     B, Hh, seq, eta = 23, 5, [0, 6], 1.0
     uv = O.synthetic_poses(B, seed=30)[:, :, :2].contiguous()
     tgt = O.synthetic_targets(O.synthetic_poses(B, seed=30), seed=31)

@@ -105,3 +105,44 @@ def test_tcg_repeatable_across_ring_wraps():
         assert torch.equal(run(), first)
     ref = D.sample(model.set_engine("fp32"), x, mask, seq, betas(), eta=1.0, noise=noise, n_hyp=Hh, repeat_input=True)
     assert (first - ref).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("tag", ["A", "A1", "B", "C"])
+def test_tcg_forward_per_sample_t(golden, tag):
+    """GCNdiff.forward (per-sample timesteps, partial key mask in B) on the tensor-core engine: close to its rounding-point
+    emulation, and to the fp32 reference within the operand precision."""
+    from _cases import build_diff
+    cfg, adj, model, sd = build_diff(tag, golden)
+    model = model.to(dev()).set_engine("tcg")
+    x, mask, tt = t(golden, f"{tag}.x"), mask_for(tag, golden), t(golden, f"{tag}.t")
+    eps = model(x.to(dev()), mask.to(dev()), tt.to(dev()), 0).cpu()
+    assert model.last_launch()[4] == 3
+    emu = E.gcndiff_forward_tcg(sd, adj, 5, 4, x, mask, tt, p16=True)
+    ref = t(golden, f"{tag}.eps")
+    scale = max(1.0, ref.abs().max().item())
+    e_emu, e_ref, amp = (eps - emu).abs().max().item(), (eps - ref).abs().max().item(), (emu - ref).abs().max().item()
+    print(f"forward {tag}: |tcg-emu|={e_emu:.2e} |tcg-ref|={e_ref:.2e} |emu-ref|={amp:.2e} scale={scale:.2f}")
+    assert e_emu < max(2e-3 * scale, amp)
+    assert e_ref < (3e-3 if tag in ("A", "A1") else 3e-2) * scale
+
+
+@pytest.mark.parametrize("tag", ["P0", "P1"])
+def test_tcg_gcnpose(golden, tag):
+    """GCNpose (uv -> xyz, no time embedding) on the tensor-core engine."""
+    from _cases import build_pose
+    cfg, adj, model, sd = build_pose(tag, golden)
+    model = model.to(dev())
+    uv = t(golden, f"{tag}.uv")
+    mask = torch.ones(1, 1, 17, dtype=torch.bool)
+    xyz = model(uv.to(dev()), mask.to(dev())).cpu()
+    assert model.engine() == "tcg" and model.last_launch()[4] == 3
+    emu = E.gcnpose_forward_tcg(sd, adj, 5, 4, uv, mask)
+    ref = t(golden, f"{tag}.xyz")
+    scale = max(1.0, ref.abs().max().item())
+    e_emu, e_ref, amp = (xyz - emu).abs().max().item(), (xyz - ref).abs().max().item(), (emu - ref).abs().max().item()
+    print(f"gcnpose {tag}: |tcg-emu|={e_emu:.2e} |tcg-ref|={e_ref:.2e} |emu-ref|={amp:.2e} scale={scale:.2f}")
+    assert e_emu < max(2e-3 * scale, amp)
+    assert e_ref < (3e-3 if tag == "P0" else 3e-2) * scale
+    # the fp32 engine stays available and exact
+    xyz32 = model.set_engine("fp32")(uv.to(dev()), mask.to(dev())).cpu()
+    assert (xyz32 - ref).abs().max().item() < 2e-5 * scale
