@@ -41,6 +41,9 @@ WORKLOADS = {
     # a slice of BASELINE.json configs[3] (1M x 10 x 50 sweep): same H and T, 16384 poses per step
     "sweep": dict(batch=16384, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
                   name="slice of configs[3]: 16384 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
+    # BASELINE.json configs[4] per GPU: GCNpose lifts uv -> xyz, root-centre, concat, H=5 hypotheses refined by GCNdiff (gt.yml seq)
+    "twostage": dict(batch=4096, n_hyp=5, seq=[0, 6], eta=0.0, two_stage=True,
+                     name="configs[4]: GCNpose (uv->xyz) + GCNdiff refinement, batch 4096, H=5, seq=[0,6] (T=2), random-init"),
 }
 
 
@@ -221,7 +224,16 @@ def main():
         noise = torch.randn(T, B * H, 17, 5, device=dev)
     targets = O.synthetic_targets(base).to(dev)
 
+    pose_model = None
+    if wl.get("two_stage"):
+        torch.manual_seed(1)
+        pose_model = D.FusedGCNpose(D.adj_mx_from_edges(), O.default_config(coords_dim=[2, 3])).to(dev).set_engine(args.engine).eval()
+        uv_pool = pool[:, :, :, :2].contiguous()
+
     def step(i):
+        if pose_model is not None:
+            return D.lift_and_refine(model, model_pose=pose_model, input_2d=uv_pool[i % pool_n], src_mask=None, seq=seq, betas=betas,
+                                     eta=eta, test_times=H)
         return D.sample(model, pool[i % pool_n], None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True,
                         mean_over_hyp=(H > 1), steps=steps_arr)
 
@@ -258,7 +270,7 @@ def main():
     host_in = [torch.empty(B, 17, 5).pin_memory() for _ in range(2)]
     host_in[0].copy_(base); host_in[1].copy_(base)
     out_rows = B if H > 1 else B * H
-    hs = D.HostStream(model, batch=B, seq=seq, betas=betas, eta=eta, test_times=H) if noise is None else None
+    hs = D.HostStream(model, batch=B, seq=seq, betas=betas, eta=eta, test_times=H) if noise is None else None    # (two-stage: times the refinement stage)
     xd = torch.empty(B, 17, 5, device=dev)
     host_out = [torch.empty(out_rows, 17, 5).pin_memory() for _ in range(2)]
 
@@ -301,7 +313,7 @@ def main():
     if rank == 0:
         peaks = load_peaks()
         per_launch_s = ms * 1e-3 / args.steps
-        flops = B * H * T * FLOP_PER_POSE_FORWARD
+        flops = B * H * T * FLOP_PER_POSE_FORWARD + (B * 25.2e6 if wl.get("two_stage") else 0.0)   # + GCNpose: 25.2 MFLOP/pose
         achieved = flops / per_launch_s / 1e12
         hbm_bytes = B * ROW_BYTES + out_rows * ROW_BYTES + (T * B * H * ROW_BYTES if noise is not None else 0)
         ll = model.last_launch()
