@@ -5,11 +5,12 @@
 //     fp32 accumulators in TMEM; biases ride along as one extra K step against a constant-one slab;
 //   * the residual stream X lives in TMEM (96 fp32 columns).  Residual additions are free: the out-projection, the
 //     second GraphNet aggregation and the b2 bias accumulate straight into those columns (D += A*B);
-//   * the 17x17 graph operators (Chebyshev T1/T2, learnable-adjacency L^).  A graph matrix G is stored once as a "tall"
-//     K-major operand [256 rows x 32] whose rows 128..144 hold G and every other row is zero; the window starting at row
-//     128-17p is the 128x32 matrix that applies G to pose p and nothing to the other poses.  The activations are
-//     consumed in place as an MN-major B operand starting at row 17p, so OUT[128 x 96] = sum_p window_p(G) *
-//     ACT[17p .. 17p+31][96] needs 14 MMAs and no data movement;
+//   * the 17x17 graph operators (Chebyshev T1/T2, learnable-adjacency L^).  Joints 0..15: a graph matrix G is stored
+//     once as a "tall" K-major operand [256 rows x 16] whose rows 128..144 hold G[:, 0:16] and every other row is zero;
+//     the window starting at row 128-18p is the 128x16 matrix that applies G to pose p and nothing to the other poses,
+//     and the activations are consumed in place as an MN-major B operand starting at row 18p: one K=16 MMA per pose.
+//     Joint 16: the epilogues also drop the joint-16 row of every pose into a compact 16-row side buffer, and one more
+//     MMA applies [G[i][16] at (18p+i, p)] to it.  OUT[128 x 96] = G per pose in 8 MMAs and no data movement;
 //   * attention: S_h = Q_h K_h^T for the whole tile (N = 128 key rows), softmax on the compute warps straight out of
 //     TMEM (each row keeps the 17 columns of its own pose), probabilities written back to TMEM as packed fp16 and used
 //     as the A operand of O_h = P_h V_h (V consumed in place as an MN-major operand);
@@ -49,7 +50,10 @@ constexpr int ABLK_BYTES = 12 * A_LBO;              // 24768
 constexpr int ONES_BYTES = 2 * A_LBO;               // 4128
 constexpr int T_ROWS = 256;                         // tall graph operand: rows 128..144 hold the matrix
 constexpr int T_LBO = T_ROWS * 16 + 16;             // 4112
-constexpr int TALL_BYTES = 4 * T_LBO;               // 16448 (K padded to 32)
+constexpr int TALL_BYTES = 2 * T_LBO;               // 8224: K = joints 0..15 (joint 16 goes through the side operands below)
+constexpr int SIDE_LBO = 256;                       // side buffer [16 rows x 96 ch]: 8-channel groups 256 B apart
+constexpr int SIDE_BYTES = 12 * SIDE_LBO;           // 3072
+constexpr int A16_BYTES = A_LBO;                    // joint-16 operand of a graph matrix: one chunk column [128 rows x 8]
 constexpr int BLOCKS_PER_LAYER = 14;
 constexpr int OUT_LBO = 256;                        // output-convolution block: N = 16 rows, K-adjacent core matrices 256 B apart
 constexpr int LP_LN_BYTES = 4 * H * 4;              // per-layer parameters: ln0_a, ln0_b, ln1_a, ln1_b (fp32)
@@ -72,7 +76,9 @@ constexpr uint32_t COL_ACC2 = 288;   // third accumulator group: GEMMs that star
 // shared memory map (bytes)
 constexpr int al16(int x) { return (x + 15) / 16 * 16; }
 constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][16] aliases block 0
-constexpr int OFF_ONES = OFF_A + 3 * ABLK_BYTES;           // constant-one K slab (bias rides in the MMA) + a zero chunk column
+constexpr int OFF_SIDE = OFF_A + 3 * ABLK_BYTES;           // per operand block: the joint-16 rows of the 7 poses, compacted (rows 7..15 zero)
+constexpr int OFF_A16 = OFF_SIDE + 3 * SIDE_BYTES;         // per graph matrix (T1, T2, L^): element (18p+i, p) = G[i][16]
+constexpr int OFF_ONES = OFF_A16 + 3 * A16_BYTES;          // constant-one K slab (bias rides in the MMA) + a zero chunk column
 constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
 constexpr int OFF_W = (OFF_TALL + 3 * TALL_BYTES + 127) / 128 * 128;
 constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][8] fp32
@@ -86,7 +92,7 @@ constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_TALL % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
               OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
@@ -309,7 +315,10 @@ __device__ __forceinline__ void wait_acc_t(Ctx& c) {
 // -> (+ temb) -> fp16 -> six 16-byte chunks of an operand block.  Deliberately NOT inlined: the layer body calls it 17
 // times, and one copy of the code keeps the loop inside the instruction cache.  All arguments travel in registers
 // (the shared-memory carve-out leaves next to no L1 for a stack).
-__device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false) {
+// side: for the joint-16 row of a pose, where its chunks go in the block's side buffer (nullptr for every other row and
+// for blocks that are never aggregated)
+__device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false,
+                                    uint8_t* side = nullptr) {
   float v[48];
   tmem_ld48(col, v);
   if (scaled) {              // row scale of an integerised graph matrix
@@ -328,13 +337,18 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
     }
   }
 #pragma unroll
-  for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + q * A_LBO) = pack8(v + 8 * q);
+  for (int q = 0; q < 6; ++q) {
+    const uint4 u = pack8(v + 8 * q);
+    *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
+    if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
+  }
 }
 
 // LayerNorm phase: residual row (48 of its 96 channels per thread) from TMEM -> LayerNorm -> fp16 operand block
 // With acol != 0 the closing residual of the previous layer's Chebyshev block is applied first: x += relu(acc), written
 // back to TMEM (later MMAs accumulate onto it).
-__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, const float* ga, const float* gb, uint32_t dst_off) {
+__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, const float* ga, const float* gb, uint32_t dst_off,
+                                   uint8_t* side = nullptr) {
   float v[48];
   if (acol != 0) {
     float u[48];
@@ -376,7 +390,11 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   }
   uint8_t* dst = smem + dst_off;
 #pragma unroll
-  for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(dst + q * A_LBO) = pack8(v + 8 * q);
+  for (int q = 0; q < 6; ++q) {
+    const uint4 u = pack8(v + 8 * q);
+    *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
+    if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
+  }
 }
 
 // x += relu(acc): the closing residual of the Chebyshev block, in TMEM
@@ -433,23 +451,21 @@ __device__ DP_PHASE_FN void softmax_run(const uint8_t* smem, uint32_t region, in
   const float inv = __frcp_rn((s0 + s1) + (s2 + s3) + sc[16]);
 #pragma unroll
   for (int j = 0; j < NP; ++j) sc[j] *= inv;
-  // P columns: K position x (= key row of the tile) belongs to pose x / 18, joint x % 18 (17 = pad, probability 0).
-  // The 64 packed columns go out as four pieces of 16; a piece none of the warp's poses touches is all zero.
+  // P[128 x 128] as the A operand of P V, 64 packed columns: slot s < 7 (columns 8s..8s+7) = joints 0..15 of pose s,
+  // slot 7 = joint 16 of poses 0..6 (K position = pose).  A row is non-zero only in its own pose's slot and position, so
+  // every pose sees the same summation order in P V, whatever its place in the tile.
+  uint32_t w[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) w[i] = pack2(sc[2 * i], sc[2 * i + 1]);
+  const uint32_t w16 = (p & 1) ? (pack2(0.f, sc[16])) : (pack2(sc[16], 0.f));
 #pragma unroll
   for (int piece = 0; piece < 4; ++piece) {
     uint32_t pk[16];
-    const int pa = (32 * piece) / PS, pb = (32 * piece + 31) / PS;      // poses this piece covers (static)
-    if (p0 + 2 >= pa && p0 <= pb) {                                      // warp-uniform
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int x0 = 32 * piece + 2 * i, x1 = x0 + 1;
-        const float e0 = (x0 % PS != NP && p == x0 / PS) ? sc[x0 % PS == NP ? 0 : x0 % PS] : 0.f;
-        const float e1 = (x1 % PS != NP && p == x1 / PS) ? sc[x1 % PS == NP ? 0 : x1 % PS] : 0.f;
-        pk[i] = pack2(e0, e1);
-      }
-    } else {
-#pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = 0u;
+    for (int i = 0; i < 16; ++i) {
+      const int col = 16 * piece + i, slot = col >> 3;
+      if (slot < TP) pk[i] = (p == slot) ? w[col & 7] : 0u;
+      else pk[i] = ((col & 7) < 4 && (p >> 1) == (col & 7)) ? w16 : 0u;
     }
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(region + 16 * piece),
@@ -506,8 +522,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   const Weights& w = *a.w;
   for (int i = tid; i < NP * NP; i += kThreads) {
     const int r = i / NP, k = i - r * NP;
-    *tall_elem(smem, 0, 128 + r, k) = __float2half_rn(__ldg(w.t1m + i));     // integer rows, exact in fp16; the row scale
-    *tall_elem(smem, 1, 128 + r, k) = __float2half_rn(__ldg(w.t2m + i));     // is applied by the epilogue
+    const __half g1 = __float2half_rn(__ldg(w.t1m + i)), g2 = __float2half_rn(__ldg(w.t2m + i));   // integer rows, exact in fp16;
+    if (k < 16) {                                                                                    // the epilogue applies the row scale
+      *tall_elem(smem, 0, 128 + r, k) = g1;
+      *tall_elem(smem, 1, 128 + r, k) = g2;
+    } else {
+      for (int p = 0; p < TP; ++p) {
+        *reinterpret_cast<__half*>(smem + OFF_A16 + (p * PS + r) * 16 + p * 2) = g1;
+        *reinterpret_cast<__half*>(smem + OFF_A16 + A16_BYTES + (p * PS + r) * 16 + p * 2) = g2;
+      }
+    }
   }
   if (tid < 32) maskf[tid] = (tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f;
   if (tid < NP) {
@@ -595,7 +619,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     auto bias = [&](uint32_t wa, uint32_t dcol) {
       umma_ss(tb + dcol, ones_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
     };
-    // D[:, dcol..dcol+96) (+)= blockdiag_p(G) * block b_blk, G = tall operand `which`
+    // D[:, dcol..dcol+96) (+)= blockdiag_p(G) * block b_blk, G = graph operand `which`: one K=16 MMA per pose over joints
+    // 0..15 (window into the tall operand x the pose's rows in place), one over the joint-16 rows in the side buffer
     auto aggregate = [&](int which, int b_blk, uint32_t dcol, uint32_t accumulate) {
       uint32_t a_lo = desc_lo(sbase + OFF_TALL + which * TALL_BYTES + 128 * 16, T_LBO);
       uint32_t b_lo = desc_lo(sbase + OFF_A + b_blk * ABLK_BYTES, 128);
@@ -603,11 +628,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
 #pragma unroll 1
       for (int p = 0; p < TP; ++p) {
         umma_ss(tb + dcol, a_lo, kHiK, b_lo, kHiActMn, kN96Mn, acc, leader);
-        umma_ss(tb + dcol, a_lo + (2 * T_LBO >> 4), kHiK, b_lo + 16, kHiActMn, kN96Mn, 1u, leader);
         acc = 1u;
         a_lo -= PS;      // window start moves up one pose (PS rows of 16 B, >> 4)
         b_lo += PS;      // activations of the next pose
       }
+      const uint32_t a16 = sbase + OFF_A16 + which * A16_BYTES;
+      umma_ss(tb + dcol, desc_lo(a16, (sbase + OFF_ONES + A_LBO) - a16), kHiK, desc_lo(sbase + OFF_SIDE + b_blk * SIDE_BYTES, 128), desc_hi(SIDE_LBO),
+              kN96Mn, 1u, leader);
     };
     // S_h[:, 0..128) = Q_h K_h^T; Q = block 0, K = block 1, chunk columns 3h..3h+2 (the 4th one of the second K step is
     // the zero chunk column behind the ones slab for Q, whatever follows for K)
@@ -617,11 +644,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       umma_ss(tb + dcol, desc_lo(qa + 2 * A_LBO, (sbase + OFF_ONES + A_LBO) - (qa + 2 * A_LBO)), kHiK, desc_lo(ka + 2 * A_LBO, A_LBO), kHiK, kN128,
               1u, leader);
     };
-    // O[:, 24h..24h+32) = P_h V[:, 24h..24h+32): P_h in TMEM at pcol (64 packed columns), V = block 2 (MN-major)
+    // O[:, 24h..24h+32) = P_h V[:, 24h..24h+32): P_h in TMEM at pcol (slot layout, see softmax_run), V = block 2 in place as an
+    // MN-major operand: one K=16 MMA per pose (joints 0..15), one for the joint-16 rows in the side buffer of block 2
     auto pv_head = [&](int h, uint32_t pcol) {
-      const uint32_t b_lo = desc_lo(sbase + OFF_A + 2 * ABLK_BYTES + 3 * h * A_LBO, 128);
+      uint32_t b_lo = desc_lo(sbase + OFF_A + 2 * ABLK_BYTES + 3 * h * A_LBO, 128);
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) umma_ts(tb + COL_O + 24 * h, tb + pcol + 8 * ks, b_lo + ks * 16, kHiActMn, kN32Mn, ks > 0 ? 1u : 0u, leader);
+      for (int p = 0; p < TP; ++p) {
+        umma_ts(tb + COL_O + 24 * h, tb + pcol + 8 * p, b_lo, kHiActMn, kN32Mn, p > 0 ? 1u : 0u, leader);
+        b_lo += PS;
+      }
+      umma_ts(tb + COL_O + 24 * h, tb + pcol + 8 * TP, desc_lo(sbase + OFF_SIDE + 2 * SIDE_BYTES + 3 * h * SIDE_LBO, 128), desc_hi(SIDE_LBO), kN32Mn, 1u,
+              leader);
     };
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int step = 0; step < a.n_steps; ++step) {
@@ -734,6 +767,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     const uint32_t my_chunk = (uint32_t)(OFF_A + a_chunk(row, hh * 6));   // its first chunk inside operand block 0
     // row scales of the integerised Chebyshev matrices for this thread's joint (pad rows: anything finite)
     const float t1scale = __ldg(w.t1s + min(row % PS, NP - 1)), t2scale = __ldg(w.t2s + min(row % PS, NP - 1));
+    // the joint-16 row of a pose also goes to the side buffer of the block it is written to (row = pose, same chunk columns)
+    uint8_t* const side0 = (row % PS == NP - 1 && row / PS < TP) ? smem + OFF_SIDE + (hh * 6) * SIDE_LBO + (row / PS) * 16 : nullptr;
+    uint8_t* const side1 = side0 ? side0 + SIDE_BYTES : nullptr;
+    uint8_t* const side2 = side0 ? side0 + 2 * SIDE_BYTES : nullptr;
 
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
@@ -793,9 +830,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             if (p < npose) tv = __ldg(reinterpret_cast<const float4*>(a.temb + ((size_t)(g0 + p) * L + l) * H) + c4);
             reinterpret_cast<float4*>(smem + OFF_TEP)[tid] = tv;
           }
-          if (tid < 4 * NP) {   // L^ into rows 128..144 of its tall operand
+          if (tid < 2 * NP) {   // L^[:, 0:16] into rows 128..144 of its tall operand
             const int kc = tid / NP, r = tid - kc * NP;
             *reinterpret_cast<uint4*>(smem + OFF_TALL + 2 * TALL_BYTES + kc * T_LBO + (128 + r) * 16) = *reinterpret_cast<const uint4*>(par + LP_LN_BYTES + tid * 16);
+          } else if (tid >= 64 && tid < 64 + TP * NP) {   // L^[:, 16] into its joint-16 operand: element (18p+i, p)
+            const int p = (tid - 64) / NP, i = (tid - 64) - p * NP;
+            *reinterpret_cast<__half*>(smem + OFF_A16 + 2 * A16_BYTES + (p * PS + i) * 16 + p * 2) =
+                *reinterpret_cast<const __half*>(par + LP_LN_BYTES + (2 * NP + i) * 16);
           }
           // The layer is a fixed sequence of compute phases, each followed by "operands ready" and a wait for the
           // accumulators of the MMA group it feeds (the issuer runs the matching program).  Straight-line code on
@@ -817,7 +858,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_run(blk0, acol, ninf, nullptr);           // q
           wait_acc(c); epi_run(blk1, acol + 96, ninf, nullptr);      // k
           signal_ready(c);                                           // q, k ready -> scores of heads 0, 1
-          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr);           // v (block 2 = LN0(x) is no longer needed)
+          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr, 1.0f, false, side2);   // v (block 2 = LN0(x) is no longer needed)
           signal_ready(c);                                           // v ready
           wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
@@ -830,7 +871,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);                                           // -> out projection (accumulates into x)
           wait_acc(c);
           // ======== x = x + GraphNet(LN1(x))
-          ln_run(smem, xcol, 0u, row, hh, lnp + 2 * H, lnp + 3 * H, my_chunk);
+          ln_run(smem, xcol, 0u, row, hh, lnp + 2 * H, lnp + 3 * H, my_chunk, side0);
           signal_ready(c);                                           // -> L^ y
           wait_acc(c);
           epi_run(blk1, acol, ninf, nullptr);
@@ -840,18 +881,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_run(blk2, acol + 96, 0.f, nullptr);
           signal_ready(c);                                           // second half
           wait_acc(c);
-          epi_run(blk1, acol2, ninf, nullptr);
+          epi_run(blk1, acol2, ninf, nullptr, 1.0f, false, side1);
           signal_ready(c);                                           // -> L^ z (accumulates into x)
           wait_acc(c);
           // ======== x = x + GC2(GC1(x) + temb)
-          epi_run(blk0, xcol, ninf, nullptr);
+          epi_run(blk0, xcol, ninf, nullptr, 1.0f, false, side0);
           signal_ready(c);                                           // x as an operand -> [T1 x | T2 x] and x Wc1_0
           wait_acc(c); epi_run(blk1, acol, ninf, nullptr, t1scale, true);
           signal_ready(c);                                           // T1 x
           wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
           signal_ready(c);                                           // T2 x
           wait_acc(c);
-          epi_run(blk0, acol2, 0.f, temb_row);
+          epi_run(blk0, acol2, 0.f, temb_row, 1.0f, false, side0);
           __syncwarp();
           if (lane == 0) mbar_arrive(pempty0 + 8 * ps);              // last use of this layer's parameters
           signal_ready(c);                                           // h = relu(GC1) + temb -> [T1 h | T2 h] and h Wc2_0
