@@ -81,8 +81,9 @@ constexpr int OFF_A16 = OFF_SIDE + 3 * SIDE_BYTES;         // per graph matrix (
 constexpr int OFF_ONES = OFF_A16 + 3 * A16_BYTES;          // constant-one K slab (bias rides in the MMA) + a zero chunk column
 constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
 constexpr int OFF_W = (OFF_TALL + 3 * TALL_BYTES + 127) / 128 * 128;
-constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][8] fp32
-constexpr int OFF_PAR = OFF_XT + TM * 8 * 4;               // per-layer parameters, 2 stages
+constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][XS] fp32
+constexpr int XS = 9;                                      // x_t row stride in floats: odd, so row-per-lane access is conflict free
+constexpr int OFF_PAR = al16(OFF_XT + TM * XS * 4);        // per-layer parameters, 2 stages
 constexpr int OFF_TEP = OFF_PAR + 2 * PAR_BYTES;           // per-pose temb [7][96] fp32 (forward mode: per-sample timesteps)
 constexpr int OFF_NBI = OFF_TEP + TP * H * 4;              // neighbour index  [17][9] int
 constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
@@ -93,7 +94,7 @@ constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
-              OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
+              OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && OFF_TEP % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -533,7 +534,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       }
     }
   }
-  if (tid < 32) maskf[tid] = (tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f;
+  if (tid < 32) maskf[tid] = (tid >= 24 && tid < 24 + a.c_out) ? __ldg(w.bout + tid - 24) : ((tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f);   // [0,17) key mask, [24,29) output bias
   if (tid < NP) {
     // neighbour list of joint tid: columns where T1 or T2 is non-zero, padded with (self, 0, 0)
     int n = 0;
@@ -760,7 +761,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     c.trace = (blockIdx.x == 0 && tid == 0) ? a.trace : nullptr;
     c.trace_n = 0; c.trace_cap = a.trace_cap / 2;
     const int row = c.row, hh = c.hh;
-    float* scratch = reinterpret_cast<float*>(smem + OFF_A);   // [128][16] fp32, aliases the head of operand block 0
+    float* scratch = reinterpret_cast<float*>(smem + OFF_A);   // [128][SCR] fp32, aliases the head of operand block 0
+    constexpr int SCR = 17;                                    // odd row stride: one thread per row reads without bank conflicts
     const bool has_mask = a.mask != nullptr;
     uint32_t ps = 0, pphase = 0;                               // parameter stage of the current layer
     const uint32_t xcol = c.tmem_lane + COL_X + hh * 48;       // this thread's half of its residual row
@@ -777,13 +779,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       const int npose = (int)min((long)TP, a.n_rows - g0);
       const int ci = a.c_in, co = a.c_out;
       const int nin = npose * NP * ci, nval = npose * NP * co;  // valid (pose, joint, coordinate) triples: input, output
-      for (int idx = tid; idx < TM * 8; idx += kComputeThreads) xt[idx] = 0.f;
+      for (int idx = tid; idx < TM * XS; idx += kComputeThreads) xt[idx] = 0.f;
       bar_compute();
       for (int idx = tid; idx < nin; idx += kComputeThreads) {
         const int p = idx / (NP * ci), rem = idx - p * (NP * ci);
         const long g = g0 + p;
         const long src = a.x_is_repeated ? g : (g % a.n_pose);
-        xt[(p * PS + rem / ci) * 8 + rem % ci] = a.x_in[src * (NP * ci) + rem];
+        xt[(p * PS + rem / ci) * XS + rem % ci] = a.x_in[src * (NP * ci) + rem];
       }
       bar_compute();
 
@@ -798,10 +800,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           const int p = r / PS, i = r - p * PS;
           if (p < TP && i < NP) {
 #pragma unroll
-            for (int cc = 0; cc < 5; ++cc) pv[cc] = xt[r * 8 + cc];
+            for (int cc = 0; cc < 5; ++cc) pv[cc] = xt[r * XS + cc];
 #pragma unroll
             for (int n = 0; n < NNB; ++n) {
-              const float* u = xt + (p * PS + nbi[i * NNB + n]) * 8;
+              const float* u = xt + (p * PS + nbi[i * NNB + n]) * XS;
               const float2 cf = nbc[i * NNB + n];
 #pragma unroll
               for (int cc = 0; cc < 5; ++cc) { pv[5 + cc] = fmaf(cf.x, u[cc], pv[5 + cc]); pv[10 + cc] = fmaf(cf.y, u[cc], pv[10 + cc]); }
@@ -933,49 +935,54 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           tmem_ld_wait();
           launder<16>(u);
 #pragma unroll
-          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(scratch + row * 16 + i) = make_float4(u[i], u[i + 1], u[i + 2], u[i + 3]);
+          for (int i = 0; i < 16; ++i) scratch[row * SCR + i] = u[i];
         }
         tc_fence_before();
         bar_compute();
         // eps = b + U0 + T1 U1 + T2 U2, then either the DDIM update (common/utils_diff.py:59-65, same operation order, no FMA
-        // contraction) or, for a plain forward call, the store of eps
+        // contraction) or, for a plain forward call, the store of eps.  Two threads per tile row: coordinates 0..2 and 3..4.
         {
           const dp_step st = a.steps_dev ? a.steps_dev[step] : inl.s[step];
-          for (int idx = tid; idx < nval; idx += kComputeThreads) {
-            const int p = idx / (NP * co), rem = idx - p * (NP * co);
-            const int i = rem / co, n = rem - i * co;
-            const int r = p * PS + i;
-            float et = __ldg(w.bout + n) + scratch[r * 16 + n];
+          const int r = tid & (TM - 1), part = tid >> 7;
+          const int p = r / PS, i = r - p * PS;
+          const int n0 = part ? 3 : 0, n1 = min(co, part ? 5 : 3);
+          if (i < NP && p < npose && n0 < n1) {
+            float et[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) et[k] = maskf[24 + n0 + k] + scratch[r * SCR + n0 + k];   // (slots past c_out are never stored)
 #pragma unroll
             for (int q = 0; q < NNB; ++q) {
-              const int rj = p * PS + nbi[i * NNB + q];
+              const float* u = scratch + (p * PS + nbi[i * NNB + q]) * SCR + n0;
               const float2 cf = nbc[i * NNB + q];
-              et = fmaf(cf.x, scratch[rj * 16 + 5 + n], et);
-              et = fmaf(cf.y, scratch[rj * 16 + 10 + n], et);
+#pragma unroll
+              for (int k = 0; k < 3; ++k) et[k] = fmaf(cf.y, u[10 + k], fmaf(cf.x, u[5 + k], et[k]));
             }
-            if (a.forward_only) {
-              a.out[(size_t)g0 * NP * co + idx] = et;
-              continue;
+            const size_t o = ((size_t)(g0 + p) * NP + i) * co;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              const int n = n0 + k;
+              if (n >= n1) break;
+              if (a.forward_only) {
+                a.out[o + n] = et[k];
+              } else {
+                const float xv = xt[r * XS + n];
+                const float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(et[k], st.sqrt_1m_at)), st.sqrt_at);
+                float nx = __fmul_rn(st.sqrt_an, x0);
+                if (a.noise) nx = __fadd_rn(nx, __fmul_rn(st.c1, a.noise[(size_t)step * a.n_rows * NP * co + o + n]));
+                xt[r * XS + n] = __fadd_rn(nx, __fmul_rn(st.c2, et[k]));
+              }
             }
-            const float xv = xt[r * 8 + n];
-            const float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(et, st.sqrt_1m_at)), st.sqrt_at);
-            float nx = __fmul_rn(st.sqrt_an, x0);
-            if (a.noise) {
-              const float z = a.noise[((size_t)step * a.n_rows + g0) * NP * co + idx];
-              nx = __fadd_rn(nx, __fmul_rn(st.c1, z));
-            }
-            xt[r * 8 + n] = __fadd_rn(nx, __fmul_rn(st.c2, et));
           }
         }
         bar_compute();
         // the scratch rows covered the 16-byte skew gaps of operand block 0: they are read (times zero) by the MN-major
         // aggregation operands, so they must hold finite fp16 again
-        if (tid < 4) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
+        if (tid < 5) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
       }
       if (!a.forward_only) {
         for (int idx = tid; idx < nval; idx += kComputeThreads) {
           const int p = idx / (NP * co), rem = idx - p * (NP * co);
-          a.out[(size_t)g0 * NP * co + idx] = xt[(p * PS + rem / co) * 8 + rem % co];
+          a.out[(size_t)g0 * NP * co + idx] = xt[(p * PS + rem / co) * XS + rem % co];
         }
       }
       bar_compute();
