@@ -170,8 +170,8 @@ def run_reference(args, wl):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=4000)   # ~0.5 s timed region: enough nvidia-smi clock samples inside it
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cpn1024", choices=sorted(WORKLOADS))
     ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc", "tcg"])

@@ -45,7 +45,6 @@ constexpr int W_LBO = 12 * 128;      // bytes between K-adjacent 8x8 core matric
 constexpr int W_SBO = 128;           // bytes between N-adjacent core matrices
 constexpr int WBLK_BYTES = (WK / 8) * W_LBO;        // 21504
 constexpr int A_LBO = 16 * 128 + 16; // 2064: chunk column stride (+16 B skews consecutive chunk columns across banks)
-constexpr int A_SBO = 128;
 constexpr int ABLK_BYTES = 12 * A_LBO;              // 24768
 constexpr int ONES_BYTES = 2 * A_LBO;               // 4128
 constexpr int T_ROWS = 256;                         // tall graph operand: rows 128..144 hold the matrix
@@ -312,10 +311,10 @@ __device__ __forceinline__ void wait_acc_t(Ctx& c) {
   trace_mark<TRACE>(c, 1);
 }
 
-// One epilogue group: 48 accumulator columns of this thread's lane: TMEM -> registers -> clamp (0 = relu, -inf = none)
-// -> (+ temb) -> fp16 -> six 16-byte chunks of an operand block.  Deliberately NOT inlined: the layer body calls it 17
-// times, and one copy of the code keeps the loop inside the instruction cache.  All arguments travel in registers
-// (the shared-memory carve-out leaves next to no L1 for a stack).
+// One epilogue group: 48 accumulator columns of this thread's lane: TMEM -> registers -> (row scale) -> clamp (lo = 0: relu,
+// -inf: none) -> (+ temb) -> fp16 -> six 16-byte chunks of an operand block.  Inlined on purpose: measured on this part, a
+// call or a taken branch to code that is not next in line costs an instruction-cache miss (100-250 cycles), and a stack
+// lives in L2 because the shared-memory carve-out leaves next to no L1.
 // side: for the joint-16 row of a pose, where its chunks go in the block's side buffer (nullptr for every other row and
 // for blocks that are never aggregated)
 __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false,
@@ -396,19 +395,6 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
     *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
     if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
   }
-}
-
-// x += relu(acc): the closing residual of the Chebyshev block, in TMEM
-__device__ DP_PHASE_FN void resid_run(uint32_t xcol, uint32_t acol) {
-  float u[48], v[48];
-  tmem_ld16_async(acol, u);
-  tmem_ld16_async(acol + 16, u + 16);
-  tmem_ld16_async(acol + 32, u + 32);
-  tmem_ld48(xcol, v);
-  launder<48>(u);
-#pragma unroll
-  for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);
-  tmem_st48(xcol, v);
 }
 
 // Softmax of one head's scores for this thread's row (GraFormer.py:104-111).  The scores of the whole tile sit in
