@@ -293,10 +293,11 @@ __device__ __forceinline__ void trace_mark(Ctx& c, int kind) {
   if (TRACE && c.trace != nullptr && c.trace_n < c.trace_cap) c.trace[c.trace_n++] = (clock64() << 1) | kind;
 }
 // "my operands are in shared memory / my TMEM accesses are done": one arrival per compute warp
-template <bool TRACE>
+// SMEM = false: the phase wrote tensor memory only (softmax), no shared-memory operand needs publishing to the async proxy
+template <bool TRACE, bool SMEM = true>
 __device__ __forceinline__ void signal_ready_t(Ctx& c) {
   trace_mark<TRACE>(c, 0);
-  fence_async_smem();
+  if (SMEM) fence_async_smem();
   tc_fence_before();
   __syncwarp();
   if (c.lane == 0) mbar_arrive(c.rdy + 8 * c.rdy_i);
@@ -472,6 +473,7 @@ __device__ __forceinline__ __half* tall_elem(uint8_t* smem, int which, int trow,
 template <bool TRACE>
 __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg inl) {
   auto signal_ready = [](Ctx& c) { signal_ready_t<TRACE>(c); };
+  auto signal_ready_tmem = [](Ctx& c) { signal_ready_t<TRACE, false>(c); };
   auto wait_acc = [](Ctx& c) { wait_acc_t<TRACE>(c); };
   extern __shared__ __align__(1024) uint8_t smem[];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -850,10 +852,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);                                           // v ready
           wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
-          signal_ready(c);                                           // -> P V of heads 0, 1; scores of heads 2, 3
+          signal_ready_tmem(c);                                      // -> P V of heads 0, 1; scores of heads 2, 3
           wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
-          signal_ready(c);                                           // -> P V of heads 2, 3
+          signal_ready_tmem(c);                                      // -> P V of heads 2, 3
           wait_acc(c);
           epi_run(blk0, ocol, ninf, nullptr);
           signal_ready(c);                                           // -> out projection (accumulates into x)
