@@ -32,6 +32,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_POSE_FORWARD = 24.65e6          # minimal algorithmic work, SURVEY.md section 8d
 ROW_BYTES = 17 * 5 * 4                   # one uvxyz pose, fp32
+NCU_DRAM_BYTES_PER_LAUNCH = 2036480      # configs[1], tc2_kernel: 2.04 MB read (weights + poses), 0 B written back (stays in L2)
 METRIC = "poses/sec, full DDIM sampling (H hyps x T steps)"
 
 WORKLOADS = {
@@ -330,7 +331,9 @@ def main():
                     "steps": e_steps, "ms_per_step": e_ms / e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": None, "peak_source": peaks["src"],
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.workload == "cpn1024" and model.engine() == "tcg") else None,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per tc2_kernel launch (profiles/r01c_ncu_tcg_metrics.csv)",
+                         "peak_source": peaks["src"],
                          "note": "achieved = 24.65 MFLOP x poses x H x T per dp_sample / mean device time of dp_sample (temb prologue + persistent kernel)",
                          "hbm_gbs": hbm_bytes / per_launch_s / 1e9},
             "clocks": clocks,

@@ -146,3 +146,27 @@ def test_tcg_gcnpose(golden, tag):
     # the fp32 engine stays available and exact
     xyz32 = model.set_engine("fp32")(uv.to(dev()), mask.to(dev())).cpu()
     assert (xyz32 - ref).abs().max().item() < 2e-5 * scale
+
+
+@pytest.mark.parametrize("n_layer", [1, 3])
+def test_tcg_other_depths(n_layer):
+    """config.model.num_layer is a runtime parameter of the tensor-core engine (weight ring, parameter ring and the issuer's
+    program all loop over it): 1 and 3 layers, every parameter perturbed, against the fp32 oracle and the emulation."""
+    cfg = O.default_config(num_layer=n_layer)
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(5)
+    model = D.FusedGCNdiff(adj, cfg)
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, seed=13)
+    model.load_state_dict(sd)
+    model = model.to(dev())
+    assert model.engine() == "tcg"
+    x = O.synthetic_poses(40, seed=17)
+    seq = [0, 8, 16]
+    g = torch.Generator().manual_seed(19)
+    noise = torch.randn(3, 40, 17, 5, generator=g)
+    ref = O.ddim_sample(x, None, seq, lambda a, m, tt: O.gcndiff_forward(sd, adj, n_layer, 4, a, m, tt), betas(), eta=1.0, noise=noise)[0][-1]
+    emu = O.ddim_sample(x, None, seq, lambda a, m, tt: E.gcndiff_forward_tcg(sd, adj, n_layer, 4, a, m, tt, p16=True), betas(), eta=1.0, noise=noise)[0][-1]
+    out = D.generalized_steps(x.to(dev()), None, seq, model, betas(), eta=1.0, noise=noise.to(dev()))[0][-1].cpu()
+    amp = (emu - ref).abs().max().item()
+    assert (out - emu).abs().max().item() < max(1e-4, amp)
+    assert (out - ref).abs().max().item() < 1e-3
