@@ -167,6 +167,37 @@ class _FusedBase(nn.Module):
         self._param_list = None
         return out
 
+    def load_checkpoint(self, path_or_states, use_ema=False, map_location="cpu"):
+        """Load a reference checkpoint: the list `[model_state_dict, optimizer_state, epoch, step, (ema_shadow)]` that
+        `runners/diffpose_frame.py:247-258` saves with `torch.save` (keys carry a `module.` prefix because the runner wraps
+        the model in DataParallel).  The reference's evaluation loads `states[0]` (`:131-132`); `use_ema=True` loads the EMA
+        shadow `states[4]` (`models/ema.py:45-49`: name -> tensor without the prefix) on top of it instead.
+        Returns (epoch, step)."""
+        states = path_or_states
+        if isinstance(states, (str, bytes)) or hasattr(states, "__fspath__"):
+            states = torch.load(states, map_location=map_location)
+        if isinstance(states, dict):          # a bare state_dict is accepted too
+            self.load_state_dict(states)
+            return None, None
+        if not isinstance(states, (list, tuple)) or len(states) < 1:
+            raise RuntimeError("load_checkpoint: expected the reference's list [state_dict, optimizer, epoch, step, (ema)]")
+        self.load_state_dict(states[0])
+        if use_ema:
+            if len(states) < 5:
+                raise RuntimeError("load_checkpoint: this checkpoint carries no EMA shadow (config.model.ema was off)")
+            shadow = {(k[7:] if k.startswith("module.") else k): v for k, v in states[4].items()}
+            own = dict(self.named_parameters())
+            missing = [k for k in shadow if k not in own]
+            if missing:
+                raise RuntimeError(f"load_checkpoint: EMA shadow has unknown parameters {missing[:3]}")
+            with torch.no_grad():
+                for k, v in shadow.items():
+                    own[k].copy_(v)
+            self.repack()
+        epoch = states[2] if len(states) > 2 else None
+        step = states[3] if len(states) > 3 else None
+        return epoch, step
+
     def set_engine(self, engine):
         """'auto' | 'fp32' | 'tc' | 'tcg' -- which kernel family runs the denoiser (see include/diffpose_b200.h)."""
         self._engine = {"auto": _lib.ENGINE_AUTO, "fp32": _lib.ENGINE_FP32, "tc": _lib.ENGINE_TC, "tcg": _lib.ENGINE_TCG}[engine]

@@ -129,3 +129,28 @@ def test_abi_library_exports_header_symbols():
         h = ctypes.c_void_p()
         rc = _lib.load().dp_create(ctypes.byref(h), 17, 5, 5, 96, 5, 4, 1)
         assert rc != 0 and b"CUDA" in _lib.load().dp_last_error()
+
+
+def test_reference_checkpoint_list_and_ema(tmp_path):
+    """runners/diffpose_frame.py:247-258 saves [state_dict (module.-prefixed), optimizer, epoch, step, ema_shadow];
+    load_checkpoint takes states[0] like the reference's evaluation (:131-132) or the EMA shadow on request."""
+    import torch
+    import diffpose_nw_b200 as D
+    from oracle import diffpose_oracle as O
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(3)
+    src = D.FusedGCNdiff(adj, O.default_config())
+    sd = {"module." + k: v.detach().clone() for k, v in src.state_dict().items()}
+    shadow = {k: v.detach().clone() * 0.5 for k, v in src.named_parameters()}      # EMAHelper.shadow: no prefix
+    path = tmp_path / "ckpt.pth"
+    torch.save([sd, {"state": {}}, 7, 1234, shadow], path)
+    torch.manual_seed(4)
+    dst = D.FusedGCNdiff(adj, O.default_config())
+    assert dst.load_checkpoint(str(path)) == (7, 1234)
+    for k, v in src.state_dict().items():
+        assert torch.equal(dst.state_dict()[k], v)
+    dst.load_checkpoint(str(path), use_ema=True)
+    for k, v in src.named_parameters():
+        assert torch.equal(dict(dst.named_parameters())[k], v * 0.5)
+    with pytest.raises(RuntimeError, match="no EMA shadow"):
+        dst.load_checkpoint([sd, {}, 1, 2], use_ema=True)
