@@ -170,3 +170,18 @@ def test_tcg_other_depths(n_layer):
     amp = (emu - ref).abs().max().item()
     assert (out - emu).abs().max().item() < max(1e-4, amp)
     assert (out - ref).abs().max().item() < 1e-3
+
+
+def test_tcg_long_schedule_steps_on_device():
+    """More than 64 DDIM steps: the step scalars no longer travel by value but through a device array."""
+    cfg = O.default_config()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev()).eval()
+    b = torch.from_numpy(O.beta_schedule("linear", 1e-4, 1e-3, 100)).float()
+    seq = list(range(0, 70))
+    x = O.synthetic_poses(20, seed=33).to(dev())
+    g = torch.Generator().manual_seed(34)
+    noise = torch.randn(len(seq), 20, 17, 5, generator=g).to(dev())
+    out = D.generalized_steps(x, None, seq, model, b, eta=1.0, noise=noise)[0][-1]
+    ref = D.generalized_steps(x, None, seq, model.set_engine("fp32"), b, eta=1.0, noise=noise)[0][-1]
+    assert torch.isfinite(out).all() and (out - ref).abs().max().item() < 1e-3
