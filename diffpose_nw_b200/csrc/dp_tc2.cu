@@ -20,8 +20,8 @@
 // Warp roles: 8 compute warps (epilogues TMEM -> registers -> fp16 operand in shared memory, LayerNorm, softmax, DDIM
 // update), one producer warp (weights and per-layer parameters L2 -> shared memory with cp.async.bulk + mbarrier
 // complete_tx, 4-stage ring of 21.5 KB blocks), one issuer warp (every tcgen05.mma, following a static per-layer
-// program).  Compute warps and issuer hand over through two mbarriers ("operands ready": 8 arrivals, "accumulator
-// ready": tcgen05.commit).
+// program).  Compute warps and issuer hand over through two 4-deep mbarrier rings ("operands ready": 8 arrivals,
+// "accumulator ready": tcgen05.commit), both sides walking the same static event sequence.
 //
 // Reference semantics: see the list at the top of dp_simt.cu (same functions, same file:line).
 #include <cuda_fp16.h>
@@ -77,7 +77,7 @@ constexpr uint32_t COL_ACC2 = 288;   // third accumulator group: GEMMs that star
 
 // shared memory map (bytes)
 constexpr int al16(int x) { return (x + 15) / 16 * 16; }
-constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][16] aliases block 0
+constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][17] aliases block 0
 constexpr int OFF_SIDE = OFF_A + 3 * ABLK_BYTES;           // per operand block: the joint-16 rows of the 7 poses, compacted (rows 7..15 zero)
 constexpr int OFF_A16 = OFF_SIDE + 3 * SIDE_BYTES;         // per graph matrix (T1, T2, L^): element (18p+i, p) = G[i][16]
 constexpr int OFF_ONES = OFF_A16 + 3 * A16_BYTES;          // constant-one K slab (bias rides in the MMA) + a zero chunk column
@@ -813,10 +813,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             }
           }
         }
-        bar_compute();
-        // the scratch rows covered the 16-byte skew gaps of operand block 0: they are read (times zero) by the MN-major
-        // aggregation operands, so they must hold finite fp16 again
-        if (tid < 5) *reinterpret_cast<uint4*>(smem + OFF_A + (tid + 1) * A_LBO - 16) = make_uint4(0, 0, 0, 0);
+        bar_compute();   // scratch (= the head of operand block 0) is free again: the next panel / epilogues overwrite it
       }
       if (!a.forward_only) {
         for (int idx = tid; idx < nval; idx += kComputeThreads) {
