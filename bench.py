@@ -42,6 +42,9 @@ WORKLOADS = {
     # a slice of BASELINE.json configs[3] (1M x 10 x 50 sweep): same H and T, 16384 poses per step
     "sweep": dict(batch=16384, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
                   name="slice of configs[3]: 16384 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
+    # one tenth of BASELINE.json configs[3] in a single call: 100 000 poses x H=10 x T=50 (17 GB of device-drawn noise)
+    "sweep100k": dict(batch=100000, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
+                      name="tenth of configs[3]: 100000 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
     # BASELINE.json configs[4] per GPU: GCNpose lifts uv -> xyz, root-centre, concat, H=5 hypotheses refined by GCNdiff (gt.yml seq)
     "twostage": dict(batch=4096, n_hyp=5, seq=[0, 6], eta=0.0, two_stage=True,
                      name="configs[4]: GCNpose (uv->xyz) + GCNdiff refinement, batch 4096, H=5, seq=[0,6] (T=2), random-init"),
