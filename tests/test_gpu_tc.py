@@ -185,3 +185,26 @@ def test_tcg_long_schedule_steps_on_device():
     out = D.generalized_steps(x, None, seq, model, b, eta=1.0, noise=noise)[0][-1]
     ref = D.generalized_steps(x, None, seq, model.set_engine("fp32"), b, eta=1.0, noise=noise)[0][-1]
     assert torch.isfinite(out).all() and (out - ref).abs().max().item() < 1e-3
+
+
+def test_trace_diagnostic_is_monotonic_and_optional():
+    """dp_set_trace: the traced kernel variant stamps every hand-over in program order; results are unchanged and the
+    production variant is used again once the buffer is cleared."""
+    cfg = O.default_config()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev()).eval()
+    x = O.synthetic_poses(14, seed=50).to(dev())
+    plain = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    buf = torch.zeros(4096, dtype=torch.int64, device=dev())
+    _lib.check(_lib.load().dp_set_trace(model._handle, buf.data_ptr(), buf.numel()), "dp_set_trace")
+    traced = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    torch.cuda.synchronize()
+    _lib.check(_lib.load().dp_set_trace(model._handle, None, 0), "dp_set_trace")
+    assert torch.equal(plain, traced)
+    raw = buf.cpu().numpy()[:2048]
+    raw = raw[raw > 0]
+    t, kind = raw >> 1, raw & 1
+    assert len(t) == 2 * (2 + 5 * 35 + 2)               # per step: input conv, 5 layers x 35 hand-over stamps, output conv
+    assert (np.diff(t) > 0).all() and kind[0] == 0 and kind[1] == 1
+    again = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert torch.equal(plain, again)
