@@ -428,10 +428,11 @@ size_t simt_smem_bytes(int H, int P) {
 template <int CL>
 int launch_simt(dp_model* m, const SimtArgs& a, const StepsArg& inl, cudaStream_t s) {
   const size_t smem = simt_smem_bytes(32 * CL, a.P);
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};          // function attributes are per device
+  bool& done = configured[m->device & 63];
+  if (!done) {
     DP_CUDA(cudaFuncSetAttribute(simt_kernel<CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
+    done = true;
   }
   const long n_tiles = (a.n_rows + a.P - 1) / a.P;
   const int grid = (int)min((long)m->sm_count, n_tiles);

@@ -808,10 +808,11 @@ int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, l
               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
               const unsigned char* mask, cudaStream_t s) {
   if (!m->tc || !m->tc->blocks) { set_error("tensor-core engine: weights are not packed"); return DP_ERR_STATE; }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};          // function attributes are per device
+  bool& done = configured[m->device & 63];
+  if (!done) {
     DP_CUDA(cudaFuncSetAttribute(tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+    done = true;
   }
   TcArgs a{};
   a.w = m->dw; a.wpack = m->tc->blocks; a.n_layer = m->d.n_layer; a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;

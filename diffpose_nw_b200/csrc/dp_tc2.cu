@@ -953,11 +953,12 @@ bool tc2_supported(const Dims& d) {
 
 static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t s) {
   if (!m->tc2 || !m->tc2->blocks) { set_error("tensor-core engine: weights are not packed"); return DP_ERR_STATE; }
-  static bool configured = false;
-  if (!configured) {
+  static bool configured[64] = {};          // function attributes are per device
+  bool& done = configured[m->device & 63];
+  if (!done) {
     DP_CUDA(cudaFuncSetAttribute(tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     DP_CUDA(cudaFuncSetAttribute(tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    configured = true;
+    done = true;
   }
   const size_t wbytes = (size_t)m->d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
   a.w = m->dw; a.wpack = m->tc2->blocks; a.ioblocks = m->tc2->blocks + wbytes; a.lparams = m->tc2->blocks + wbytes + 2 * WBLK_BYTES;

@@ -126,3 +126,22 @@ def test_host_stream_matches_direct_calls():
         assert g.shape == w.shape and torch.equal(g, w)
     with pytest.raises(RuntimeError, match="exceeds"):
         hs.submit(O.synthetic_poses(65).pin_memory())
+
+
+def test_second_device_in_one_process():
+    """A model on cuda:1 while cuda:0 is current (DataParallel-style use): per-device kernel attributes and device guards."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    torch.manual_seed(0)
+    cfg = O.default_config()
+    m0 = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to("cuda:0").eval()
+    torch.manual_seed(0)
+    m1 = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to("cuda:1").eval()
+    x = O.synthetic_poses(30, seed=70)
+    a = D.generalized_steps(x.to("cuda:0"), None, [0, 12], m0, betas())[0][-1]
+    torch.cuda.set_device(0)
+    b = D.generalized_steps(x.to("cuda:1"), None, [0, 12], m1, betas())[0][-1]
+    assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
+    for eng in ("fp32", "tc"):
+        c = D.generalized_steps(x.to("cuda:1"), None, [0, 12], m1.set_engine(eng), betas())[0][-1]
+        assert (c.cpu() - a.cpu()).abs().max().item() < 1e-3
