@@ -215,25 +215,24 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   } else {
     tmem_ld48(xcol, v);
   }
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-  for (int i = 0; i < 48; i += 4) { s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3]; }
-  const float m = ((s0 + s1) + (s2 + s3)) * (1.0f / 48.0f);
-  float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+  // one pass: sum and sum of squares of this thread's 48 channels (fp32; the row has 96 values of comparable size, so the
+  // cancellation in sum(x^2) - n mean^2 costs a few ulp of the variance -- far below the fp16 rounding of the output)
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 48; i += 4) {
-    const float d0 = v[i] - m, d1 = v[i + 1] - m, d2 = v[i + 2] - m, d3 = v[i + 3] - m;
-    q0 = fmaf(d0, d0, q0); q1 = fmaf(d1, d1, q1); q2 = fmaf(d2, d2, q2); q3 = fmaf(d3, d3, q3);
+    s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3];
+    q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1); q2 = fmaf(v[i + 2], v[i + 2], q2); q3 = fmaf(v[i + 3], v[i + 3], q3);
   }
-  const float qq = (q0 + q1) + (q2 + q3);
+  const float sh = (s0 + s1) + (s2 + s3), qh = (q0 + q1) + (q2 + q3);
   float2* stat = reinterpret_cast<float2*>(smem + OFF_STAT);
-  stat[hh * TM + row] = make_float2(m, qq);
+  stat[hh * TM + row] = make_float2(sh, qh);
   bar_compute();
   const float2 o = stat[(hh ^ 1) * TM + row];
-  const float mean = 0.5f * (m + o.x);
-  const float dm = m - o.x;
-  const float m2 = qq + o.y + dm * dm * 24.0f;
-  const float inv = __frcp_rn(sqrtf(m2 * (1.0f / (float)(H - 1))) + 1e-6f);
+  const float mean = (sh + o.x) * (1.0f / (float)H);
+  const float m2 = fmaxf(fmaf(-(sh + o.x), mean, qh + o.y), 0.f);          // sum (x - mean)^2
+  float sd;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(m2 * (1.0f / (float)(H - 1))));
+  const float inv = __frcp_rn(sd + 1e-6f);
 #pragma unroll
   for (int q = 0; q < 12; ++q) {
     const float4 a = *reinterpret_cast<const float4*>(ga + hh * 48 + 4 * q), b = *reinterpret_cast<const float4*>(gb + hh * 48 + 4 * q);
