@@ -20,8 +20,9 @@
 // Warp roles: 8 compute warps (epilogues TMEM -> registers -> fp16 operand in shared memory, LayerNorm, softmax, DDIM
 // update), one producer warp (weights and per-layer parameters L2 -> shared memory with cp.async.bulk + mbarrier
 // complete_tx, 4-stage ring of 21.5 KB blocks), one issuer warp (every tcgen05.mma, following a static per-layer
-// program).  Compute warps and issuer hand over through two 4-deep mbarrier rings ("operands ready": 8 arrivals,
-// "accumulator ready": tcgen05.commit), both sides walking the same static event sequence.
+// program).  Compute warps and issuer hand over through two 4-deep event rings, both sides walking the same static
+// sequence: "operands ready" = hardware named barriers (bar.arrive by the 256 compute threads, bar.sync by the issuer warp:
+// measurably faster to wake than an mbarrier), "accumulator ready" = mbarriers armed by tcgen05.commit.
 //
 // Reference semantics: see the list at the top of dp_simt.cu (same functions, same file:line).
 #include <cuda_fp16.h>
@@ -91,7 +92,7 @@ constexpr int OFF_NBI = OFF_TEP + TP * H * 4;              // neighbour index  [
 constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
 constexpr int OFF_STAT = al16(OFF_NBC + NP * NNB * 8);     // LayerNorm partial statistics [2][128] float2
 constexpr int OFF_MASK = OFF_STAT + 2 * TM * 8;            // key mask [32]
-constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], rdy[4], acc[4]
+constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], (unused)[4], acc[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
@@ -150,8 +151,8 @@ __device__ __forceinline__ void signal_ready_t(Ctx& c) {
   trace_mark<TRACE>(c, 0);
   if (SMEM) fence_async_smem();
   tc_fence_before();
-  __syncwarp();
-  if (c.lane == 0) mbar_arrive(c.rdy + 8 * c.rdy_i);
+  // hardware named barrier 2 + ring slot: 256 compute threads arrive, the issuer warp (32 threads) waits
+  asm volatile("bar.arrive %0, 288;" ::"r"(2 + c.rdy_i) : "memory");
   c.rdy_i = (c.rdy_i + 1) & (NEV - 1);
 }
 template <bool TRACE>
@@ -431,9 +432,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     auto imark = [&]() { if (TRACE && itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
     auto wait_rdy = [&]() {
       imark();
-      mbar_wait(rdy + 8 * rdy_i, rdy_phase);
+      asm volatile("bar.sync %0, 288;" ::"r"(2 + rdy_i) : "memory");
       rdy_i = (rdy_i + 1) & (NEV - 1);
-      if (rdy_i == 0) rdy_phase ^= 1;
       tc_fence_after();
       imark();
     };
