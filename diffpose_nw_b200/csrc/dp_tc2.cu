@@ -500,8 +500,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         uint32_t wa;
         // 0. x = [x_t | T1 x_t | T2 x_t] Win + b at hi/lo precision: A = block 0 chunk columns 0..5 (hi, lo, hi),
         //    B = [Win_hi ; Win_hi ; Win_lo] (row 15 of each slab carries the bias)
+        wa = w_acquire();     // (before the wait: the weights are there long before the operands)
         wait_rdy();
-        wa = w_acquire();
         {
           const uint32_t a_lo = desc_lo(sbase + OFF_A, A_LBO), b_lo = desc_lo(wa, W_LBO);
 #pragma unroll
@@ -516,8 +516,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           // ACC+96 (also the two score regions), ACC2 and the O region, arranged so that a GEMM may start while the
           // compute warps are still reading the groups of the previous one.
           // 1. q, k, v = LN0(x) W + b                         A = block 2; one event per output block
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 2, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+          wait_rdy(); gemm(wa, 2, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
           wa = w_acquire(); gemm(wa, 2, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
           wa = w_acquire(); gemm(wa, 2, COL_O, 0u); bias(wa, COL_O); w_release(); commit_acc();
           // 1b. attention, two heads at a time: S = Q_h K_h^T (d_k = 24 = K step of 16 + 8 real | 8 zero columns),
@@ -534,22 +534,22 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           pv_head(2, COL_S0); pv_head(3, COL_S1);
           commit_acc();
           // 2. x += attn Wo + bo                              A = block 0
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 0, COL_X, 1u); bias(wa, COL_X); w_release();
+          wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+          wait_rdy(); gemm(wa, 0, COL_X, 1u); bias(wa, COL_X); w_release();
           commit_acc();
           // 3. g1 = L^ LN1(x)                                 B = block 0
           wait_rdy();
           aggregate(2, 0, COL_ACC, 0u);
           commit_acc();
           // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1; one event per half
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 1, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+          wait_rdy(); gemm(wa, 1, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
           wa = w_acquire(); gemm(wa, 1, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
           // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2, each as soon as its half of h is there
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_X); w_release();
-          wait_rdy();
-          wa = w_acquire(); gemm(wa, 2, COL_ACC2, 1u); w_release();
+          wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+          wait_rdy(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_X); w_release();
+          wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+          wait_rdy(); gemm(wa, 2, COL_ACC2, 1u); w_release();
           commit_acc();
           // 6. x += L^ z                                      B = block 1
           wait_rdy();
@@ -562,16 +562,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             aggregate(0, 0, COL_ACC, 0u); commit_acc();
             aggregate(1, 0, COL_ACC + 96, 0u); commit_acc();
             wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_ACC2); w_release();
-            wait_rdy();
-            wa = w_acquire(); gemm(wa, 1, COL_ACC2, 1u); w_release();
-            wait_rdy();
-            wa = w_acquire(); gemm(wa, 2, COL_ACC2, 1u); w_release();
+            wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+            wait_rdy(); gemm(wa, 1, COL_ACC2, 1u); w_release();
+            wa = w_acquire();     // (before the wait: the weights are there long before the operands)
+            wait_rdy(); gemm(wa, 2, COL_ACC2, 1u); w_release();
             commit_acc();
           }
         }
         // 11. U = [X_hi | X_lo | X_hi] [Wout_hi ; Wout_hi ; Wout_lo]   (N = 16: 3 Chebyshev orders x 5 outputs)
+        wa = w_acquire();     // (before the wait: the weights are there long before the operands)
         wait_rdy();
-        wa = w_acquire();
         {
           const uint32_t b_lo = desc_lo(wa, OUT_LBO);
 #pragma unroll
@@ -657,11 +657,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           *reinterpret_cast<uint4*>(dst + a_chunk(r, 4)) = h0; *reinterpret_cast<uint4*>(dst + a_chunk(r, 5)) = h1;
         }
         signal_ready(c);                                           // -> 0
+        mbar_wait(pfull0 + 8 * ps, pphase);                        // layer 0's parameters (checked here, off the critical path)
         wait_acc(c);
 
         for (int l = 0; l < L; ++l) {
           // this layer's parameters (LayerNorm gains, L^, temb) have been staged by the producer
-          mbar_wait(pfull0 + 8 * ps, pphase);
           const uint8_t* par = smem + OFF_PAR + ps * PAR_BYTES;
           const float* lnp = reinterpret_cast<const float*>(par);
           if (a.forward_only && a.has_temb && tid < TP * (H / 4)) {   // per-sample timesteps: this layer's temb row of every pose
@@ -740,8 +740,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);
           wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
           signal_ready(c);
-          wait_acc(c);                                               // GC2 in ACC2: the residual is applied by the next phase
           if (++ps == 2) { ps = 0; pphase ^= 1; }
+          if (l + 1 < L) mbar_wait(pfull0 + 8 * ps, pphase);        // the next layer's parameters, while the last GEMM runs
+          wait_acc(c);                                               // GC2 in ACC2: the residual is applied by the next phase
         }
 
         // ---- output ChebConv (N = 5): U_k = X Wout_k on the tensor cores with X = hi + lo, then
