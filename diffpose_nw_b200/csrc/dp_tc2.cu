@@ -639,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           if (p < TP && i < NP) {
 #pragma unroll
             for (int cc = 0; cc < 5; ++cc) pv[cc] = xt[r * XS + cc];
-#pragma unroll
+#pragma unroll 1
             for (int n = 0; n < NNB; ++n) {
               const float* u = xt + (p * PS + nbi[i * NNB + n]) * XS;
               const float2 cf = nbc[i * NNB + n];
@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             float et[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) et[k] = maskf[24 + n0 + k] + scratch[r * SCR + n0 + k];   // (slots past c_out are never stored)
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < NNB; ++q) {
               const float* u = scratch + (p * PS + nbi[i * NNB + q]) * SCR + n0;
               const float2 cf = nbc[i * NNB + q];
