@@ -45,6 +45,9 @@ WORKLOADS = {
     # one tenth of BASELINE.json configs[3] in a single call: 100 000 poses x H=10 x T=50 (17 GB of device-drawn noise)
     "sweep100k": dict(batch=100000, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
                       name="tenth of configs[3]: 100000 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
+    # BASELINE.json configs[3] itself when run on 8 GPUs: 1M poses x H=10 x T=50 in total, 125 000 poses per rank and call
+    "sweep1m_over8": dict(batch=125000, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
+                          name="configs[3] at 8 ranks: 125000 poses per rank x H=10 x T=50 (1M poses in total on 8 GPUs), eta=1 with device noise, random-init"),
     # BASELINE.json configs[4] per GPU: GCNpose lifts uv -> xyz, root-centre, concat, H=5 hypotheses refined by GCNdiff (gt.yml seq)
     "twostage": dict(batch=4096, n_hyp=5, seq=[0, 6], eta=0.0, two_stage=True,
                      name="configs[4]: GCNpose (uv->xyz) + GCNdiff refinement, batch 4096, H=5, seq=[0,6] (T=2), random-init"),
