@@ -171,14 +171,14 @@ __device__ __forceinline__ void wait_acc_t(Ctx& c) {
 // side: for the joint-16 row of a pose, where its chunks go in the block's side buffer (nullptr for every other row and
 // for blocks that are never aggregated)
 __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false,
-                                    uint8_t* side = nullptr) {
+                                    uint8_t* side = nullptr, bool relu_in_cvt = false) {
   float v[48];
   tmem_ld48(col, v);
   if (scaled) {              // row scale of an integerised graph matrix
 #pragma unroll
-    for (int i = 0; i < 48; ++i) v[i] *= scale;
+    for (int i = 0; i < 48; i += 2) mul2(v[i], v[i + 1], v[i], v[i + 1], scale, scale);
   }
-  if (lo == 0.f) {
+  if (lo == 0.f && !relu_in_cvt) {
 #pragma unroll
     for (int i = 0; i < 48; ++i) v[i] = fmaxf(v[i], 0.f);
   }
@@ -186,12 +186,13 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
 #pragma unroll
     for (int i = 0; i < 48; i += 4) {
       const float4 t = *reinterpret_cast<const float4*>(temb + i);
-      v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+      add2(v[i], v[i + 1], v[i], v[i + 1], t.x, t.y);
+      add2(v[i + 2], v[i + 3], v[i + 2], v[i + 3], t.z, t.w);
     }
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
-    const uint4 u = pack8(v + 8 * q);
+    const uint4 u = relu_in_cvt ? pack8_relu(v + 8 * q) : pack8(v + 8 * q);
     *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
     if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
   }
@@ -211,7 +212,7 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
     tmem_ld48(xcol, v);
     launder<48>(u);
 #pragma unroll
-    for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);
+    for (int i = 0; i < 48; i += 2) add2(v[i], v[i + 1], v[i], v[i + 1], fmaxf(u[i], 0.f), fmaxf(u[i + 1], 0.f));
     tmem_st48(xcol, v);
   } else {
     tmem_ld48(xcol, v);
@@ -221,8 +222,10 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
 #pragma unroll
   for (int i = 0; i < 48; i += 4) {
-    s0 += v[i]; s1 += v[i + 1]; s2 += v[i + 2]; s3 += v[i + 3];
-    q0 = fmaf(v[i], v[i], q0); q1 = fmaf(v[i + 1], v[i + 1], q1); q2 = fmaf(v[i + 2], v[i + 2], q2); q3 = fmaf(v[i + 3], v[i + 3], q3);
+    add2(s0, s1, s0, s1, v[i], v[i + 1]);
+    add2(s2, s3, s2, s3, v[i + 2], v[i + 3]);
+    fma2(q0, q1, v[i], v[i + 1], v[i], v[i + 1], q0, q1);
+    fma2(q2, q3, v[i + 2], v[i + 3], v[i + 2], v[i + 3], q2, q3);
   }
   const float sh = (s0 + s1) + (s2 + s3), qh = (q0 + q1) + (q2 + q3);
   float2* stat = reinterpret_cast<float2*>(smem + OFF_STAT);
@@ -234,11 +237,18 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   float sd;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(m2 * (1.0f / (float)(H - 1))));
   const float inv = __frcp_rn(sd + 1e-6f);
+  const float nmean = -mean;
+  // a_2 (x - mean) / (std + eps) + b_2 as x g + (b_2 - mean g), g = a_2 / (std + eps): three packed operations per pair
 #pragma unroll
   for (int q = 0; q < 12; ++q) {
     const float4 a = *reinterpret_cast<const float4*>(ga + hh * 48 + 4 * q), b = *reinterpret_cast<const float4*>(gb + hh * 48 + 4 * q);
-    v[4 * q] = fmaf(a.x * inv, v[4 * q] - mean, b.x); v[4 * q + 1] = fmaf(a.y * inv, v[4 * q + 1] - mean, b.y);
-    v[4 * q + 2] = fmaf(a.z * inv, v[4 * q + 2] - mean, b.z); v[4 * q + 3] = fmaf(a.w * inv, v[4 * q + 3] - mean, b.w);
+    float g0, g1, g2, g3, h0, h1, h2, h3;
+    mul2(g0, g1, a.x, a.y, inv, inv);
+    mul2(g2, g3, a.z, a.w, inv, inv);
+    fma2(h0, h1, nmean, nmean, g0, g1, b.x, b.y);
+    fma2(h2, h3, nmean, nmean, g2, g3, b.z, b.w);
+    fma2(v[4 * q], v[4 * q + 1], v[4 * q], v[4 * q + 1], g0, g1, h0, h1);
+    fma2(v[4 * q + 2], v[4 * q + 3], v[4 * q + 2], v[4 * q + 3], g2, g3, h2, h3);
   }
   uint8_t* dst = smem + dst_off;
 #pragma unroll
@@ -716,9 +726,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c);
           epi_run(blk1, acol, ninf, nullptr);
           signal_ready(c);                                           // -> fc1
-          wait_acc(c); epi_run(blk0, acol, 0.f, nullptr);
+          wait_acc(c); epi_run(blk0, acol, 0.f, nullptr, 1.0f, false, nullptr, true);
           signal_ready(c);                                           // first half of relu(h) -> fc2, first K block
-          wait_acc(c); epi_run(blk2, acol + 96, 0.f, nullptr);
+          wait_acc(c); epi_run(blk2, acol + 96, 0.f, nullptr, 1.0f, false, nullptr, true);
           signal_ready(c);                                           // second half
           wait_acc(c);
           epi_run(blk1, acol2, ninf, nullptr, 1.0f, false, side1);
