@@ -59,10 +59,11 @@ constexpr int SIDE_BYTES = 12 * SIDE_LBO;           // 3072
 constexpr int A16_BYTES = A_LBO;                    // joint-16 operand of a graph matrix: one chunk column [128 rows x 8]
 constexpr int BLOCKS_PER_LAYER = 14;
 constexpr int OUT_LBO = 256;                        // output-convolution block: N = 16 rows, K-adjacent core matrices 256 B apart
-constexpr int LP_LN_BYTES = 4 * H * 4;              // per-layer parameters: ln0_a, ln0_b, ln1_a, ln1_b (fp32)
-constexpr int LP_LHAT_BYTES = 4 * NP * 16;          //   + L^ as fp16 [4 chunk columns][17 rows][8]
-constexpr int LP_BYTES = LP_LN_BYTES + LP_LHAT_BYTES;   // 2624, copied from the packed parameter array
-constexpr int PAR_BYTES = LP_BYTES + H * 4;         // + temb of this (step, layer): 3008 per stage
+constexpr int LP_LHAT_BYTES = 4 * NP * 16;          // per-layer parameters: L^ as fp16 [4 chunk columns][17 rows][8]
+constexpr int LP_JS_BYTES = PS * 16;                //   + the joint slab rows (1, 1, r_hi, r_hi, r_lo, 0, 0, 0), r = row sums of L^
+constexpr int LP_BYTES = LP_LHAT_BYTES + LP_JS_BYTES;   // 1376, copied from the packed parameter array
+constexpr int PAR_BYTES = LP_BYTES + H * 4;         // + temb of this (step, layer): 1760 per stage
+constexpr int JS_BYTES = TM * 16;                   // joint slab: one chunk column [128 rows x 8]
 constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
 constexpr int kComputeThreads = 256;
 constexpr int kProducerWarp = 8, kIssuerWarp = 9;
@@ -81,7 +82,8 @@ constexpr int al16(int x) { return (x + 15) / 16 * 16; }
 constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][17] aliases block 0
 constexpr int OFF_SIDE = OFF_A + 3 * ABLK_BYTES;           // per operand block: the joint-16 rows of the 7 poses, compacted (rows 7..15 zero)
 constexpr int OFF_A16 = OFF_SIDE + 3 * SIDE_BYTES;         // per graph matrix (T1, T2, L^): element (18p+i, p) = G[i][16]
-constexpr int OFF_ONES = OFF_A16 + 3 * A16_BYTES;          // constant-one K slab (bias rides in the MMA) + a zero chunk column
+constexpr int OFF_JS = OFF_A16 + 3 * A16_BYTES;            // joint slab of the current layer (fc1 bias + the LayerNorm shift seen through L^)
+constexpr int OFF_ONES = OFF_JS + JS_BYTES;                // constant-one K slab (bias rides in the MMA) + a zero chunk column
 constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
 constexpr int OFF_W = (OFF_TALL + 3 * TALL_BYTES + 127) / 128 * 128;
 constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][XS] fp32
@@ -96,7 +98,7 @@ constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
               OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && OFF_TEP % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -201,8 +203,7 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
 // LayerNorm phase: residual row (48 of its 96 channels per thread) from TMEM -> LayerNorm -> fp16 operand block
 // With acol != 0 the closing residual of the previous layer's Chebyshev block is applied first: x += relu(acc), written
 // back to TMEM (later MMAs accumulate onto it).
-__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, const float* ga, const float* gb, uint32_t dst_off,
-                                   uint8_t* side = nullptr) {
+__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, uint32_t dst_off, uint8_t* side = nullptr) {
   float v[48];
   if (acol != 0) {
     float u[48];
@@ -213,7 +214,9 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
     launder<48>(u);
 #pragma unroll
     for (int i = 0; i < 48; i += 2) add2(v[i], v[i + 1], v[i], v[i + 1], fmaxf(u[i], 0.f), fmaxf(u[i + 1], 0.f));
-    tmem_st48(xcol, v);
+    tmem_st16(xcol, v);            // completion is awaited at the end of the phase, behind the LayerNorm arithmetic
+    tmem_st16(xcol + 16, v + 16);
+    tmem_st16(xcol + 32, v + 32);
   } else {
     tmem_ld48(xcol, v);
   }
@@ -237,19 +240,11 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   float sd;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(m2 * (1.0f / (float)(H - 1))));
   const float inv = __frcp_rn(sd + 1e-6f);
-  const float nmean = -mean;
-  // a_2 (x - mean) / (std + eps) + b_2 as x g + (b_2 - mean g), g = a_2 / (std + eps): three packed operations per pair
+  // (x - mean) / (std + eps): the gains a_2, b_2 are folded into the weights and biases of the GEMMs that consume this
+  // operand (tc2_pack), so nothing is read from shared memory here -- the phase is bound by shared-memory bandwidth
+  const float shift = -mean * inv;
 #pragma unroll
-  for (int q = 0; q < 12; ++q) {
-    const float4 a = *reinterpret_cast<const float4*>(ga + hh * 48 + 4 * q), b = *reinterpret_cast<const float4*>(gb + hh * 48 + 4 * q);
-    float g0, g1, g2, g3, h0, h1, h2, h3;
-    mul2(g0, g1, a.x, a.y, inv, inv);
-    mul2(g2, g3, a.z, a.w, inv, inv);
-    fma2(h0, h1, nmean, nmean, g0, g1, b.x, b.y);
-    fma2(h2, h3, nmean, nmean, g2, g3, b.z, b.w);
-    fma2(v[4 * q], v[4 * q + 1], v[4 * q], v[4 * q + 1], g0, g1, h0, h1);
-    fma2(v[4 * q + 2], v[4 * q + 3], v[4 * q + 2], v[4 * q + 3], g2, g3, h2, h3);
-  }
+  for (int i = 0; i < 48; i += 2) fma2(v[i], v[i + 1], v[i], v[i + 1], inv, inv, shift, shift);
   uint8_t* dst = smem + dst_off;
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -257,6 +252,7 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
     *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
     if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
   }
+  if (acol != 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
 // Softmax of one head's scores for this thread's row (GraFormer.py:104-111).  The scores of the whole tile sit in
@@ -289,17 +285,21 @@ __device__ DP_PHASE_FN void softmax_run(const uint8_t* smem, uint32_t region, in
   float m0 = fmaxf(sc[0], sc[1]), m1 = fmaxf(sc[2], sc[3]), m2 = fmaxf(sc[4], sc[5]), m3 = fmaxf(sc[6], sc[7]);
   m0 = fmaxf(m0, fmaxf(sc[8], sc[9])); m1 = fmaxf(m1, fmaxf(sc[10], sc[11])); m2 = fmaxf(m2, fmaxf(sc[12], sc[13])); m3 = fmaxf(m3, fmaxf(sc[14], sc[15]));
   const float mk = fmaxf(fmaxf(m0, m1), fmaxf(fmaxf(m2, m3), sc[16])) * k2;
+  const float nmk = -mk;
   float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
   for (int j = 0; j < 16; j += 4) {
-    sc[j] = ex2(fmaf(sc[j], k2, -mk)); sc[j + 1] = ex2(fmaf(sc[j + 1], k2, -mk));
-    sc[j + 2] = ex2(fmaf(sc[j + 2], k2, -mk)); sc[j + 3] = ex2(fmaf(sc[j + 3], k2, -mk));
-    s0 += sc[j]; s1 += sc[j + 1]; s2 += sc[j + 2]; s3 += sc[j + 3];
+    fma2(sc[j], sc[j + 1], sc[j], sc[j + 1], k2, k2, nmk, nmk);
+    fma2(sc[j + 2], sc[j + 3], sc[j + 2], sc[j + 3], k2, k2, nmk, nmk);
+    sc[j] = ex2(sc[j]); sc[j + 1] = ex2(sc[j + 1]); sc[j + 2] = ex2(sc[j + 2]); sc[j + 3] = ex2(sc[j + 3]);
+    add2(s0, s1, s0, s1, sc[j], sc[j + 1]);
+    add2(s2, s3, s2, s3, sc[j + 2], sc[j + 3]);
   }
-  sc[16] = ex2(fmaf(sc[16], k2, -mk));
+  sc[16] = ex2(fmaf(sc[16], k2, nmk));
   const float inv = __frcp_rn((s0 + s1) + (s2 + s3) + sc[16]);
 #pragma unroll
-  for (int j = 0; j < NP; ++j) sc[j] *= inv;
+  for (int j = 0; j < 16; j += 2) mul2(sc[j], sc[j + 1], sc[j], sc[j + 1], inv, inv);
+  sc[16] *= inv;
   // P[128 x 128] as the A operand of P V, 64 packed columns: slot s < 7 (columns 8s..8s+7) = joints 0..15 of pose s,
   // slot 7 = joint 16 of poses 0..6 (K position = pose).  A row is non-zero only in its own pose's slot and position, so
   // every pose sees the same summation order in P V, whatever its place in the tile.
@@ -402,7 +402,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   // let the next kernel of the stream begin its launch: its CTAs take over each SM as ours retire
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const long n_tiles = (a.n_rows + TP - 1) / TP;
+  const int n_tiles = (int)((a.n_rows + TP - 1) / TP);   // the host refuses more than INT_MAX tiles
   const int L = a.n_layer;
 
   if (warp == kProducerWarp) {
@@ -416,7 +416,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         bulk_g2s(sbase + OFF_W + stage * WBLK_BYTES, src, WBLK_BYTES, full0 + 8 * stage);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       };
-      for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
         for (int step = 0; step < a.n_steps; ++step) {
           put_block(a.ioblocks);
           for (int l = 0; l < L; ++l) {
@@ -468,6 +468,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     auto bias = [&](uint32_t wa, uint32_t dcol) {
       umma_ss(tb + dcol, ones_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
     };
+    // the same with the joint slab as A: bias + r_i * beta (k = 98..100 of the block), second chunk column = the zero one
+    const uint32_t js_lo = desc_lo(sbase + OFF_JS, OFF_ONES + A_LBO - OFF_JS);
+    auto bias_joint = [&](uint32_t wa, uint32_t dcol) {
+      umma_ss(tb + dcol, js_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
+    };
     // D[:, dcol..dcol+96) (+)= blockdiag_p(G) * block b_blk, G = graph operand `which`: one K=16 MMA per pose over joints
     // 0..15 (window into the tall operand x the pose's rows in place), one over the joint-16 rows in the side buffer
     auto aggregate = [&](int which, int b_blk, uint32_t dcol, uint32_t accumulate) {
@@ -505,7 +510,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       umma_ts(tb + COL_O + 24 * h, tb + pcol + 8 * TP, desc_lo(sbase + OFF_SIDE + 2 * SIDE_BYTES + 3 * h * SIDE_LBO, 128), desc_hi(SIDE_LBO), kN32Mn, 1u,
               leader);
     };
-    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
       for (int step = 0; step < a.n_steps; ++step) {
         uint32_t wa;
         // 0. x = [x_t | T1 x_t | T2 x_t] Win + b at hi/lo precision: A = block 0 chunk columns 0..5 (hi, lo, hi),
@@ -553,8 +558,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           commit_acc();
           // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1; one event per half
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-          wait_rdy(); gemm(wa, 1, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
-          wa = w_acquire(); gemm(wa, 1, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
+          wait_rdy(); gemm(wa, 1, COL_ACC, 0u); bias_joint(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire(); gemm(wa, 1, COL_ACC + 96, 0u); bias_joint(wa, COL_ACC + 96); w_release(); commit_acc();
           // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2, each as soon as its half of h is there
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
           wait_rdy(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_X); w_release();
@@ -622,8 +627,8 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     uint8_t* const side1 = side0 ? side0 + SIDE_BYTES : nullptr;
     uint8_t* const side2 = side0 ? side0 + 2 * SIDE_BYTES : nullptr;
 
-    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long g0 = tile * TP;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long g0 = (long)tile * TP;
       const int npose = (int)min((long)TP, a.n_rows - g0);
       const int ci = a.c_in, co = a.c_out;
       const int nin = npose * NP * ci, nval = npose * NP * co;  // valid (pose, joint, coordinate) triples: input, output
@@ -673,7 +678,6 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         for (int l = 0; l < L; ++l) {
           // this layer's parameters (LayerNorm gains, L^, temb) have been staged by the producer
           const uint8_t* par = smem + OFF_PAR + ps * PAR_BYTES;
-          const float* lnp = reinterpret_cast<const float*>(par);
           if (a.forward_only && a.has_temb && tid < TP * (H / 4)) {   // per-sample timesteps: this layer's temb row of every pose
             const int p = tid / (H / 4), c4 = tid - p * (H / 4);
             float4 tv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -682,12 +686,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           }
           if (tid < 2 * NP) {   // L^[:, 0:16] into rows 128..144 of its tall operand
             const int kc = tid / NP, r = tid - kc * NP;
-            *reinterpret_cast<uint4*>(smem + OFF_TALL + 2 * TALL_BYTES + kc * T_LBO + (128 + r) * 16) = *reinterpret_cast<const uint4*>(par + LP_LN_BYTES + tid * 16);
+            *reinterpret_cast<uint4*>(smem + OFF_TALL + 2 * TALL_BYTES + kc * T_LBO + (128 + r) * 16) = *reinterpret_cast<const uint4*>(par + tid * 16);
           } else if (tid >= 64 && tid < 64 + TP * NP) {   // L^[:, 16] into its joint-16 operand: element (18p+i, p)
             const int p = (tid - 64) / NP, i = (tid - 64) - p * NP;
             *reinterpret_cast<__half*>(smem + OFF_A16 + 2 * A16_BYTES + (p * PS + i) * 16 + p * 2) =
-                *reinterpret_cast<const __half*>(par + LP_LN_BYTES + (2 * NP + i) * 16);
+                *reinterpret_cast<const __half*>(par + (2 * NP + i) * 16);
           }
+          if (tid < TR)     // joint slab of this layer (the previous layer's fc1 finished reading it long ago)
+            *reinterpret_cast<uint4*>(smem + OFF_JS + tid * 16) = *reinterpret_cast<const uint4*>(par + LP_LHAT_BYTES + (tid % PS) * 16);
           // The layer is a fixed sequence of compute phases, each followed by "operands ready" and a wait for the
           // accumulators of the MMA group it feeds (the issuer runs the matching program).  Straight-line code on
           // purpose: on this part every taken branch to code that is not next in line costs an instruction-cache miss.
@@ -703,7 +709,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
                                   : (a.forward_only ? reinterpret_cast<const float*>(smem + OFF_TEP) + min(row / PS, TP - 1) * H
                                                     : reinterpret_cast<const float*>(par + LP_BYTES)) + hh * 48;
           // ======== x = x + attn(LN0(x))   (first the closing residual of the previous layer's Chebyshev block)
-          ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, lnp, lnp + H, my_chunk + 2 * ABLK_BYTES);
+          ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, my_chunk + 2 * ABLK_BYTES);
           signal_ready(c);                                           // LN0(x) in block 2
           wait_acc(c); epi_run(blk0, acol, ninf, nullptr);           // q
           wait_acc(c); epi_run(blk1, acol + 96, ninf, nullptr);      // k
@@ -721,7 +727,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);                                           // -> out projection (accumulates into x)
           wait_acc(c);
           // ======== x = x + GraphNet(LN1(x))
-          ln_run(smem, xcol, 0u, row, hh, lnp + 2 * H, lnp + 3 * H, my_chunk, side0);
+          ln_run(smem, xcol, 0u, row, hh, my_chunk, side0);
           signal_ready(c);                                           // -> L^ y
           wait_acc(c);
           epi_run(blk1, acol, ninf, nullptr);
@@ -841,22 +847,35 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   if (ktrace) ktrace[3] = clock64();
 }
 
+__device__ __forceinline__ float hi16(float v) { return __half2float(__float2half_rn(v)); }
+
 // fp32 [K][N] panels of the fp32 blob -> fp16 weight block in the canonical K-major no-swizzle UMMA layout.
 // block element (n, k): n in [0,96) output feature, k in [0,112): k < 96 weight W[k0+k][n0+n]; k = 96/97 bias hi/lo.
+// A LayerNorm in front of the GEMM is folded in (GraFormer.py:67-70: y = a_2 n + b_2 with n the normalised row): the weight
+// rows are scaled by a_2, and the shift b_2 W goes
+//   fold = 1: into the bias (the GEMM reads y directly: q, k, v);
+//   fold = 2: into rows k = 98..100 as (hi, lo, hi) of beta = b_2 W, to be multiplied by the joint slab (r_hi, r_hi, r_lo):
+//             the GEMM reads L^ y = (L^ n) a_2 + r b_2^T, r = row sums of L^ (fc1 of the GraphNet).
 __global__ void tc2_pack_block_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int ldw, int k0, int n0,
-                                      const float* __restrict__ bias) {
+                                      const float* __restrict__ bias, const float* __restrict__ ln_a, const float* __restrict__ ln_b, int fold) {
   for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 96 * WK; idx += gridDim.x * blockDim.x) {
     const int n = idx / WK, k = idx - n * WK;
     float v = 0.f;
-    if (k < 96) v = W[(size_t)(k0 + k) * ldw + n0 + n];
-    else if (bias != nullptr && k == 96) v = __half2float(__float2half_rn(bias[n]));
-    else if (bias != nullptr && k == 97) { const float b = bias[n]; v = b - __half2float(__float2half_rn(b)); }
+    if (k < 96) {
+      v = W[(size_t)(k0 + k) * ldw + n0 + n];
+      if (fold) v *= ln_a[k0 + k];
+    } else if (k <= 100) {
+      float beta = 0.f;
+      if (fold) for (int j = 0; j < 96; ++j) beta = fmaf(ln_b[k0 + j], W[(size_t)(k0 + j) * ldw + n0 + n], beta);
+      const float b = (bias != nullptr ? bias[n] : 0.f) + (fold == 1 ? beta : 0.f);
+      if (k == 96) v = hi16(b);
+      else if (k == 97) v = b - hi16(b);
+      else if (fold == 2) v = (k == 99) ? beta - hi16(beta) : hi16(beta);
+    }
     const size_t off = (size_t)(k >> 3) * W_LBO + (size_t)(n >> 3) * W_SBO + (n & 7) * 16 + (k & 7) * 2;
     *reinterpret_cast<__half*>(dst + off) = __float2half_rn(v);
   }
 }
-
-__device__ __forceinline__ float hi16(float v) { return __half2float(__float2half_rn(v)); }
 
 // Input convolution block [N=96][K=48]: K slabs [hi ; hi ; lo] of the panel weights Win [3*c_in][96]; panel position
 // k = order*5 + coordinate (coordinates >= c_in are zero), the bias sits in row 15.
@@ -887,16 +906,22 @@ __global__ void tc2_pack_io_kernel(uint8_t* __restrict__ dst, const float* __res
   }
 }
 
-// per-layer parameter record: ln0_a, ln0_b, ln1_a, ln1_b (fp32) then L^ as fp16 [4 chunk columns][17 rows][8]
-__global__ void tc2_pack_lparams_kernel(uint8_t* __restrict__ dst, const float* ln0a, const float* ln0b, const float* ln1a, const float* ln1b,
-                                        const float* __restrict__ lhat) {
-  float* f = reinterpret_cast<float*>(dst);
-  for (int i = threadIdx.x; i < H; i += blockDim.x) { f[i] = ln0a[i]; f[H + i] = ln0b[i]; f[2 * H + i] = ln1a[i]; f[3 * H + i] = ln1b[i]; }
-  __half* hp = reinterpret_cast<__half*>(dst + LP_LN_BYTES);
+// per-layer parameter record: L^ as fp16 [4 chunk columns][17 rows][8], then the joint slab rows [18][8]:
+// (1, 1, r_hi, r_hi, r_lo, 0, 0, 0) with r_i = sum_j L^[i][j] in fp32 (row 17, the pad row of a pose, is zero)
+__global__ void tc2_pack_lparams_kernel(uint8_t* __restrict__ dst, const float* __restrict__ lhat) {
+  __half* hp = reinterpret_cast<__half*>(dst);
   for (int i = threadIdx.x; i < 4 * NP * 8; i += blockDim.x) {
     const int kc = i / (NP * 8), r = (i / 8) % NP, e = i & 7;
     const int k = kc * 8 + e;
     hp[i] = __float2half_rn(k < NP ? lhat[r * NP + k] : 0.f);
+  }
+  __half* js = reinterpret_cast<__half*>(dst + LP_LHAT_BYTES);
+  for (int i = threadIdx.x; i < PS; i += blockDim.x) {
+    float r = 0.f;
+    if (i < NP) for (int j = 0; j < NP; ++j) r += lhat[i * NP + j];
+    const float one = i < NP ? 1.f : 0.f, rh = hi16(r);
+    const float vals[8] = {one, one, rh, rh, r - rh, 0.f, 0.f, 0.f};
+    for (int e = 0; e < 8; ++e) js[i * 8 + e] = __float2half_rn(i < NP ? vals[e] : 0.f);
   }
 }
 
@@ -916,8 +941,9 @@ void tc2_free(dp_model* m) {
 }
 
 // `bias` points at the first of the 96 bias values of this block (or NULL)
-static int pack_block(uint8_t* dst, const float* W, int ldw, int k0, int n0, const float* bias, cudaStream_t s) {
-  tc2_pack_block_kernel<<<12, 256, 0, s>>>(dst, W, ldw, k0, n0, bias);
+static int pack_block(uint8_t* dst, const float* W, int ldw, int k0, int n0, const float* bias, cudaStream_t s, const float* ln_a = nullptr,
+                      const float* ln_b = nullptr, int fold = 0) {
+  tc2_pack_block_kernel<<<12, 256, 0, s>>>(dst, W, ldw, k0, n0, bias, ln_a, ln_b, fold);
   count_launch();
   DP_CUDA(cudaGetLastError());
   return DP_OK;
@@ -941,13 +967,13 @@ int tc2_pack(dp_model* m, cudaStream_t s) {
     int i = 0;
     // consumption order of the issuer: q, k, v, o, fc1 (two output halves), fc2 (two input halves; the first carries b2,
     // which the kernel adds to the residual stream), cheb1 x3, cheb2 x3
-    for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wqkv, 3 * H, 0, part * H, L.bqkv + part * H, s));
+    for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wqkv, 3 * H, 0, part * H, L.bqkv + part * H, s, L.ln0_a, L.ln0_b, 1));
     DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wo, H, 0, 0, L.bo, s));
-    for (int part = 0; part < 2; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.w1, 2 * H, 0, part * H, L.b1 + part * H, s));
+    for (int part = 0; part < 2; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.w1, 2 * H, 0, part * H, L.b1 + part * H, s, L.ln1_a, L.ln1_b, 2));
     for (int part = 0; part < 2; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.w2, H, part * H, 0, part == 0 ? L.b2 : nullptr, s));
     for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wc1, H, part * H, 0, part == 0 ? L.bc1 : nullptr, s));
     for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * WBLK_BYTES, L.wc2, H, part * H, 0, part == 0 ? L.bc2 : nullptr, s));
-    tc2_pack_lparams_kernel<<<1, 128, 0, s>>>(m->tc2->blocks + wbytes + 2 * WBLK_BYTES + (size_t)l * LP_BYTES, L.ln0_a, L.ln0_b, L.ln1_a, L.ln1_b, L.lhat);
+    tc2_pack_lparams_kernel<<<1, 128, 0, s>>>(m->tc2->blocks + wbytes + 2 * WBLK_BYTES + (size_t)l * LP_BYTES, L.lhat);
     count_launch();
     DP_CUDA(cudaGetLastError());
   }
@@ -976,6 +1002,7 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
   a.temb = m->temb;
   a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
+  if (n_tiles > 0x7fffffffL) { set_error("tensor-core engine: more than 2^31 tiles of 7 poses in one call"); return DP_ERR_INVALID; }
   const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;

@@ -103,8 +103,13 @@ def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
     d_k = hid // n_head
     for l in range(n_layer):
         p, g = f"atten_layers.{l}", f"gconv_layers.{l}"
-        y = r16(O.layer_norm(X, sd[f"{p}.sublayer.0.norm.a_2"], sd[f"{p}.sublayer.0.norm.b_2"]))
-        q, k, v = (r16(y @ r16(sd[f"{p}.self_attn.linears.{i}.weight"]).T + split16(sd[f"{p}.self_attn.linears.{i}.bias"])) for i in range(3))
+        # LayerNorm gains folded into the consumers (csrc/dp_tc2.cu tc2_pack_block_kernel): the operand is the plain
+        # normalised row, the weights are a_2-scaled before the fp16 rounding, the shift b_2 W joins the bias
+        one, zero = torch.ones(hid), torch.zeros(hid)
+        a0, b0 = sd[f"{p}.sublayer.0.norm.a_2"], sd[f"{p}.sublayer.0.norm.b_2"]
+        y = r16(O.layer_norm(X, one, zero))
+        q, k, v = (r16(y @ r16(a0[:, None] * sd[f"{p}.self_attn.linears.{i}.weight"].T)
+                       + split16(sd[f"{p}.self_attn.linears.{i}.bias"] + b0 @ sd[f"{p}.self_attn.linears.{i}.weight"].T)) for i in range(3))
         nb = X.shape[0]
         qh, kh, vh = (u.view(nb, -1, n_head, d_k).transpose(1, 2) for u in (q, k, v))
         sc = torch.matmul(qh, kh.transpose(-2, -1)) / math.sqrt(d_k)
@@ -118,10 +123,15 @@ def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
         # GraphNet sublayer: aggregate, fc1, relu, fc2, aggregate (+ b2 straight onto the residual stream)
         a_hat = sd[f"{p}.feed_forward.A_hat"]
         dd = (a_hat.sum(0) + 1e-5) ** (-0.5)
-        lhat = r16(dd.view(-1, 1) * a_hat * dd.view(1, -1))
-        y = r16(O.layer_norm(X, sd[f"{p}.sublayer.1.norm.a_2"], sd[f"{p}.sublayer.1.norm.b_2"]))
+        lhat32 = dd.view(-1, 1) * a_hat * dd.view(1, -1)
+        lhat = r16(lhat32)
+        # L^ (a_2 n + b_2) W1 = (L^ n)(a_2 W1) + r (b_2 W1), r = row sums of L^ (fp32; enters through the joint slab)
+        a1, b1 = sd[f"{p}.sublayer.1.norm.a_2"], sd[f"{p}.sublayer.1.norm.b_2"]
+        w1 = sd[f"{p}.feed_forward.gconv1.fc.weight"]
+        y = r16(O.layer_norm(X, one, zero))
         g1 = r16(torch.matmul(lhat, y))
-        h = r16(torch.relu(g1 @ r16(sd[f"{p}.feed_forward.gconv1.fc.weight"]).T + split16(sd[f"{p}.feed_forward.gconv1.fc.bias"])))
+        h = r16(torch.relu(g1 @ r16(a1[:, None] * w1.T) + split16(sd[f"{p}.feed_forward.gconv1.fc.bias"])
+                           + lhat32.sum(1).view(1, -1, 1) * (b1 @ w1.T).view(1, 1, -1)))
         z = r16(h @ r16(sd[f"{p}.feed_forward.gconv2.fc.weight"]).T)
         X = X + torch.matmul(lhat, z) + split16(sd[f"{p}.feed_forward.gconv2.fc.bias"])
         # residual Chebyshev block

@@ -26,11 +26,15 @@ def _models():
     return adj, diff, sd_d, pose, sd_p
 
 
-@pytest.mark.parametrize("engine", ["fp32", "auto"])
+@pytest.mark.parametrize("engine", ["fp32", "auto", "mixed"])
 def test_two_stage_pipeline_vs_oracle(engine):
+    """mixed = fp32 lifter + tensor-core denoiser.  The denoiser's fp16-operand error reaches x damped by the DDIM
+    coefficients (a few 1e-5 here); the lifter's output IS the xyz input, undamped, so with these random weights
+    (|xyz| up to 2) a tensor-core lifter alone costs up to ~2e-3 (oracle/tc_emulation.py predicts the same figure)."""
     dev = torch.device("cuda:0")
     adj, diff, sd_d, pose, sd_p = _models()
-    diff, pose = diff.to(dev).set_engine(engine), pose.to(dev).set_engine(engine)
+    diff = diff.to(dev).set_engine("auto" if engine == "mixed" else engine)
+    pose = pose.to(dev).set_engine("fp32" if engine == "mixed" else engine)
     B, Hh, seq, eta = 23, 5, [0, 6], 1.0
     uv = O.synthetic_poses(B, seed=30)[:, :, :2].contiguous()
     tgt = O.synthetic_targets(O.synthetic_poses(B, seed=30), seed=31)
@@ -47,7 +51,7 @@ def test_two_stage_pipeline_vs_oracle(engine):
     # product
     out = D.lift_and_refine(diff, model_pose=pose, input_2d=uv.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(),
                             eta=eta, test_times=Hh, noise=noise.to(dev))
-    tol = 2e-5 if diff.engine() == "fp32" else 1e-3
+    tol = {"fp32": 2e-5, "mixed": 1e-3, "auto": 3e-3}[engine]
     assert (out.cpu() - ref).abs().max().item() < tol
     sums = D.evaluate_shard(diff, None, tgt.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(), eta=eta, test_times=Hh,
                             noise=noise.to(dev), model_pose=pose, input_2d=uv.to(dev), batch_size=10)
