@@ -359,6 +359,7 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
     for (int i = 0; same && i < n_steps; ++i) same = (h->temb_t[i] == steps_host[i].t);
     if (!same) {
       DP_TRY(simt_temb(h, steps_dev ? &steps_dev->t : nullptr, sizeof(dp_step) / sizeof(float), &inl, n_steps, s));
+      if (tc2_supported(d)) DP_TRY(tc2_tau(h, n_steps, s));
       h->temb_t.resize(n_steps);
       for (int i = 0; i < n_steps; ++i) h->temb_t[i] = steps_host[i].t;
     }

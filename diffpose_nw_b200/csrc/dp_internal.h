@@ -133,6 +133,8 @@ void tc_lab_cycles(long long* out2);
 bool tc2_supported(const Dims& d);
 int tc2_forward(dp_model* m, const float* x, const float* t, const unsigned char* mask, float* out, long n, cudaStream_t s);
 int tc2_pack(dp_model* m, cudaStream_t s);
+// after simt_temb filled m->temb for a sampler schedule: the same embeddings as GC2 bias blocks of the tcg engine
+int tc2_tau(dp_model* m, int n_steps, cudaStream_t s);
 void tc2_free(dp_model* m);
 int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
                const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,

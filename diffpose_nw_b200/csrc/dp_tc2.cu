@@ -62,7 +62,8 @@ constexpr int OUT_LBO = 256;                        // output-convolution block:
 constexpr int LP_LHAT_BYTES = 4 * NP * 16;          // per-layer parameters: L^ as fp16 [4 chunk columns][17 rows][8]
 constexpr int LP_JS_BYTES = PS * 16;                //   + the joint slab rows (1, 1, r_hi, r_hi, r_lo, 0, 0, 0), r = row sums of L^
 constexpr int LP_BYTES = LP_LHAT_BYTES + LP_JS_BYTES;   // 1376, copied from the packed parameter array
-constexpr int PAR_BYTES = LP_BYTES + H * 4;         // + temb of this (step, layer): 1760 per stage
+constexpr int LP_TAU_BYTES = H * 16;                // time-embedding block of one (step, layer): [96 outputs][8] fp16 (tc2_tau_kernel)
+constexpr int PAR_BYTES = LP_BYTES + LP_TAU_BYTES;  // 2912 per stage
 constexpr int JS_BYTES = TM * 16;                   // joint slab: one chunk column [128 rows x 8]
 constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
 constexpr int kComputeThreads = 256;
@@ -82,7 +83,8 @@ constexpr int al16(int x) { return (x + 15) / 16 * 16; }
 constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][17] aliases block 0
 constexpr int OFF_SIDE = OFF_A + 3 * ABLK_BYTES;           // per operand block: the joint-16 rows of the 7 poses, compacted (rows 7..15 zero)
 constexpr int OFF_A16 = OFF_SIDE + 3 * SIDE_BYTES;         // per graph matrix (T1, T2, L^): element (18p+i, p) = G[i][16]
-constexpr int OFF_JS = OFF_A16 + 3 * A16_BYTES;            // joint slab of the current layer (fc1 bias + the LayerNorm shift seen through L^)
+constexpr int OFF_CS = OFF_A16 + 3 * A16_BYTES;            // Chebyshev slab: rows (1, 1, p1_hi, p1_hi, p1_lo, p2_hi, p2_hi, p2_lo), p_k = row sums of T_k
+constexpr int OFF_JS = OFF_CS + JS_BYTES;                  // joint slab of the current layer (fc1 bias + the LayerNorm shift seen through L^)
 constexpr int OFF_ONES = OFF_JS + JS_BYTES;                // constant-one K slab (bias rides in the MMA) + a zero chunk column
 constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
 constexpr int OFF_W = (OFF_TALL + 3 * TALL_BYTES + 127) / 128 * 128;
@@ -98,7 +100,7 @@ constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_CS % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
               OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && OFF_TEP % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -122,7 +124,8 @@ struct Tc2Args {
   float* out;
   long n_rows, n_pose;
   int n_steps;
-  const float* temb;         // [n_steps][n_layer][96], or [n_rows][n_layer][96] (per-sample timesteps) when forward_only
+  const float* temb;         // [n_rows][n_layer][96]: per-sample time embeddings of a forward call (forward_only)
+  const uint8_t* tau;        // [n_steps][n_layer][LP_TAU_BYTES]: the sampler's time embedding as a bias block of GC2 (tc2_tau)
   const float* noise;
   const unsigned char* mask;
   const dp_step* steps_dev;
@@ -383,6 +386,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       }
     }
   }
+  if (tid < TR && tid % PS < NP) {
+    // Chebyshev slab (static): GC2 sees h + 1 temb^T, and T_k (1 temb^T) = p_k temb^T with p_k the row sums of T_k
+    // (p_0 = 1; for a row-normalised adjacency p_1 = 0, p_2 = -1, but nothing here relies on it)
+    const int i = tid % PS;
+    float p1 = 0.f, p2 = 0.f;
+    for (int j = 0; j < NP; ++j) { p1 += __ldg(w.t1 + i * NP + j); p2 += __ldg(w.t2 + i * NP + j); }
+    const float p1h = __half2float(__float2half_rn(p1)), p2h = __half2float(__float2half_rn(p2));
+    *reinterpret_cast<uint4*>(smem + OFF_CS + tid * 16) = make_uint4(pack2(1.f, 1.f), pack2(p1h, p1h), pack2(p1 - p1h, p2h), pack2(p2h, p2 - p2h));
+  }
   if (tid < 32) maskf[tid] = (tid >= 24 && tid < 24 + a.c_out) ? __ldg(w.bout + tid - 24) : ((tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f);   // [0,17) key mask, [24,29) output bias
   if (tid < NP) {
     // neighbour list of joint tid: columns where T1 or T2 is non-zero, padded with (self, 0, 0)
@@ -424,7 +436,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             const bool step_temb = !a.forward_only && a.has_temb;     // one temb row per (step, layer), shared by the batch
             mbar_expect_tx(pfull0 + 8 * ps, step_temb ? PAR_BYTES : LP_BYTES);
             bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES, a.lparams + (size_t)l * LP_BYTES, LP_BYTES, pfull0 + 8 * ps);
-            if (step_temb) bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES + LP_BYTES, a.temb + ((size_t)step * L + l) * H, H * 4, pfull0 + 8 * ps);
+            if (step_temb) bulk_g2s(sbase + OFF_PAR + ps * PAR_BYTES + LP_BYTES, a.tau + ((size_t)step * L + l) * LP_TAU_BYTES, LP_TAU_BYTES, pfull0 + 8 * ps);
             if (++ps == 2) { ps = 0; pphase ^= 1; }
             for (int blk = 0; blk < BLOCKS_PER_LAYER; ++blk) put_block(a.wpack + ((size_t)l * BLOCKS_PER_LAYER + blk) * WBLK_BYTES);
           }
@@ -470,6 +482,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     };
     // the same with the joint slab as A: bias + r_i * beta (k = 98..100 of the block), second chunk column = the zero one
     const uint32_t js_lo = desc_lo(sbase + OFF_JS, OFF_ONES + A_LBO - OFF_JS);
+    // sampler: the time embedding enters GC2 as one more K step, A = Chebyshev slab, B = this (step, layer)'s block in the
+    // parameter stage (its second chunk column repeats the first: LBO = 0; the slab's second one is the zero column)
+    const uint32_t cs_lo = desc_lo(sbase + OFF_CS, OFF_ONES + A_LBO - OFF_CS);
+    const bool tau_step = a.has_temb && !a.forward_only;
+    uint32_t ips = 0, ipphase = 0;
     auto bias_joint = [&](uint32_t wa, uint32_t dcol) {
       umma_ss(tb + dcol, js_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
     };
@@ -572,17 +589,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           commit_acc();
           // 7/8, 9/10. the two Chebyshev convolutions: [T1 v | T2 v] (B = block 0, one event each), and
           //     [v | T1 v | T2 v] Wc + b into ACC2 -- the v part right away, the others as their operands arrive
+          if (tau_step) { mbar_wait(pfull0 + 8 * ips, ipphase); tc_fence_after(); }   // complete long ago: the compute warps waited on it
           for (int conv = 0; conv < 2; ++conv) {
             wait_rdy();
             aggregate(0, 0, COL_ACC, 0u); commit_acc();
             aggregate(1, 0, COL_ACC + 96, 0u); commit_acc();
-            wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_ACC2); w_release();
+            wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_ACC2);
+            if (conv == 1 && tau_step) umma_ss(tb + COL_ACC2, cs_lo, kHiK, desc_lo(sbase + OFF_PAR + ips * PAR_BYTES + LP_BYTES, 0), kHiK, kN96, 1u, leader);
+            w_release();
             wa = w_acquire();     // (before the wait: the weights are there long before the operands)
             wait_rdy(); gemm(wa, 1, COL_ACC2, 1u); w_release();
             wa = w_acquire();     // (before the wait: the weights are there long before the operands)
             wait_rdy(); gemm(wa, 2, COL_ACC2, 1u); w_release();
             commit_acc();
           }
+          if (++ips == 2) { ips = 0; ipphase ^= 1; }
         }
         // 11. U = [X_hi | X_lo | X_hi] [Wout_hi ; Wout_hi ; Wout_lo]   (N = 16: 3 Chebyshev orders x 5 outputs)
         wa = w_acquire();     // (before the wait: the weights are there long before the operands)
@@ -703,11 +724,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           uint8_t* const blk2 = blk0 + 2 * ABLK_BYTES;
           const float ninf = -INFINITY;
           const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48, ocol = c.tmem_lane + COL_O + hh * 48;
-          // temb added after GC1 (gcndiff.py:51): one row per (step, layer) in the sampler, one per pose in a forward call,
-          // none for GCNpose
-          const float* temb_row = !a.has_temb ? nullptr
-                                  : (a.forward_only ? reinterpret_cast<const float*>(smem + OFF_TEP) + min(row / PS, TP - 1) * H
-                                                    : reinterpret_cast<const float*>(par + LP_BYTES)) + hh * 48;
+          // temb added after GC1 (gcndiff.py:51).  Sampler: the issuer adds it to GC2 as a bias block, nothing to do here.
+          // Forward call: one row per pose, added in the epilogue.  GCNpose: none.
+          const bool pose_temb = a.forward_only && a.has_temb;
+          const float* temb_row = reinterpret_cast<const float*>(smem + OFF_TEP) + min(row / PS, TP - 1) * H + hh * 48;
           // ======== x = x + attn(LN0(x))   (first the closing residual of the previous layer's Chebyshev block)
           ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, my_chunk + 2 * ABLK_BYTES);
           signal_ready(c);                                           // LN0(x) in block 2
@@ -748,17 +768,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
           signal_ready(c);                                           // T2 x
           wait_acc(c);
-          epi_run(blk0, acol2, 0.f, temb_row, 1.0f, false, side0);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(pempty0 + 8 * ps);              // last use of this layer's parameters
-          signal_ready(c);                                           // h = relu(GC1) + temb -> [T1 h | T2 h] and h Wc2_0
+          if (pose_temb) epi_run(blk0, acol2, 0.f, temb_row, 1.0f, false, side0);
+          else epi_run(blk0, acol2, 0.f, nullptr, 1.0f, false, side0, true);
+          signal_ready(c);                                           // h = relu(GC1) (+ temb) -> [T1 h | T2 h] and h Wc2_0
           wait_acc(c); epi_run(blk1, acol, ninf, nullptr, t1scale, true);
           signal_ready(c);
           wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
           signal_ready(c);
+          const uint32_t ps_done = ps;
           if (++ps == 2) { ps = 0; pphase ^= 1; }
           if (l + 1 < L) mbar_wait(pfull0 + 8 * ps, pphase);        // the next layer's parameters, while the last GEMM runs
           wait_acc(c);                                               // GC2 in ACC2: the residual is applied by the next phase
+          __syncwarp();
+          if (lane == 0) mbar_arrive(pempty0 + 8 * ps_done);         // GC2 was the last reader of this layer's parameter stage
         }
 
         // ---- output ChebConv (N = 5): U_k = X Wout_k on the tensor cores with X = hi + lo, then
@@ -925,16 +947,53 @@ __global__ void tc2_pack_lparams_kernel(uint8_t* __restrict__ dst, const float* 
   }
 }
 
+// Time embedding of the sampler as a bias block of GC2 (gcndiff.py:48-53: GC2(relu(GC1 x) + temb)):
+// sum_k T_k (1 temb^T) W_k = sum_k p_k (temb^T W_k), p_k = row sums of T_k (the Chebyshev slab of the kernel).
+// One block per (step, layer): [96 outputs][8] = (u0_hi, u0_lo, u1_hi, u1_lo, u1_hi, u2_hi, u2_lo, u2_hi), u_k = temb^T W_k.
+__global__ void tc2_tau_kernel(uint8_t* __restrict__ dst, const float* __restrict__ temb, const Weights* __restrict__ w, int n_layer) {
+  const float* t = temb + (size_t)blockIdx.x * H;          // table rows are [step][layer]
+  const float* wc2 = w->layer[blockIdx.x % n_layer].wc2;
+  const int n = threadIdx.x;
+  float u[3];
+  for (int k = 0; k < 3; ++k) {
+    float acc = 0.f;
+    for (int c = 0; c < H; ++c) acc = fmaf(t[c], wc2[(size_t)(k * H + c) * H + n], acc);
+    u[k] = acc;
+  }
+  const float h0 = hi16(u[0]), h1 = hi16(u[1]), h2 = hi16(u[2]);
+  *reinterpret_cast<uint4*>(dst + (size_t)blockIdx.x * LP_TAU_BYTES + n * 16) =
+      make_uint4(pack2(h0, u[0] - h0), pack2(h1, u[1] - h1), pack2(h1, h2), pack2(u[2] - h2, h2));
+}
+
 }  // namespace
 
 struct Tc2Pack {
   uint8_t* blocks = nullptr;   // [n_layer][14][WBLK_BYTES] then [2][WBLK_BYTES] (io blocks) then [n_layer][LP_BYTES]
   size_t bytes = 0;
+  uint8_t* tau = nullptr;      // [n_steps][n_layer][LP_TAU_BYTES] of the cached schedule
+  size_t tau_bytes = 0;
 };
+
+// m->temb holds the [n_steps][n_layer][96] table of the schedule (simt_temb): derive the GC2 bias blocks from it
+int tc2_tau(dp_model* m, int n_steps, cudaStream_t s) {
+  if (!m->tc2 || !m->d.has_temb) return DP_OK;
+  const size_t need = (size_t)n_steps * m->d.n_layer * LP_TAU_BYTES;
+  if (m->tc2->tau_bytes < need) {
+    if (m->tc2->tau) cudaFree(m->tc2->tau);
+    m->tc2->tau = nullptr; m->tc2->tau_bytes = 0;
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tc2->tau), need));
+    m->tc2->tau_bytes = need;
+  }
+  tc2_tau_kernel<<<n_steps * m->d.n_layer, H, 0, s>>>(m->tc2->tau, m->temb, m->dw, m->d.n_layer);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
 
 void tc2_free(dp_model* m) {
   if (m->tc2) {
     if (m->tc2->blocks) cudaFree(m->tc2->blocks);
+    if (m->tc2->tau) cudaFree(m->tc2->tau);
     delete m->tc2;
     m->tc2 = nullptr;
   }
@@ -999,7 +1058,7 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
   const size_t wbytes = (size_t)m->d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
   a.w = m->dw; a.wpack = m->tc2->blocks; a.ioblocks = m->tc2->blocks + wbytes; a.lparams = m->tc2->blocks + wbytes + 2 * WBLK_BYTES;
   a.n_layer = m->d.n_layer; a.c_in = m->d.c_in; a.c_out = m->d.c_out; a.has_temb = m->d.has_temb;
-  a.temb = m->temb;
+  a.temb = m->temb; a.tau = m->tc2->tau;
   a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   if (n_tiles > 0x7fffffffL) { set_error("tensor-core engine: more than 2^31 tiles of 7 poses in one call"); return DP_ERR_INVALID; }

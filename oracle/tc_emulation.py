@@ -79,11 +79,13 @@ def gcnpose_forward_tcg(sd, adj, n_layer, n_head, x, mask, p16=True):
     return gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, None, p16=p16)
 
 
-def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
+def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False, temb_in_gc2=False):
     """Rounding points of the second-generation tcgen05 engine (csrc/dp_tc2.cu): every tensor-core operand is fp16 --
     activations, weights and the learnable 17x17 matrix L^, which the kernel applies as per-pose MMAs; the Chebyshev
     matrices T1, T2 are applied exactly (integer rows in fp16 times an fp32 row scale, csrc/dp_api.cu integerise_rows);
-    accumulation, the residual stream (TMEM), LayerNorm statistics and softmax are fp32.  Differences from the
+    accumulation, the residual stream (TMEM), LayerNorm statistics and softmax are fp32.  temb_in_gc2: the sampler's form --
+    the batch-uniform time embedding is not added to the hidden activation before its fp16 rounding but enters GC2 as
+    the bias sum_k rowsum(T_k) (temb^T W_k) (dp_forward with per-sample timesteps keeps the addition).  Differences from the
     reference order: fc2 is commuted in front of the second L^ aggregation (L^(h W2) + b2), and the Chebyshev input
     panel is [x16 | r16(T1 x16) | r16(T2 x16)].  p16: attention probabilities are fp16 operands too."""
     hid = sd["gconv_input.weight"].shape[-1]
@@ -136,8 +138,15 @@ def gcndiff_forward_tcg(sd, adj, n_layer, n_head, x, mask, t, p16=False):
         X = X + torch.matmul(lhat, z) + split16(sd[f"{p}.feed_forward.gconv2.fc.bias"])
         # residual Chebyshev block
         h1 = torch.relu(cheb_tc(r16(X), sd[f"{g}.gconv1.gconv.weight"], sd[f"{g}.gconv1.gconv.bias"]))
+        tau = 0.0
         if temb is not None:
-            h1 = h1 + torch.nn.functional.linear(O.swish(temb), sd[f"{g}.temb_proj.weight"], sd[f"{g}.temb_proj.bias"])[:, None, :]
-        h2 = torch.relu(cheb_tc(r16(h1), sd[f"{g}.gconv2.gconv.weight"], sd[f"{g}.gconv2.gconv.bias"]))
+            tp = torch.nn.functional.linear(O.swish(temb), sd[f"{g}.temb_proj.weight"], sd[f"{g}.temb_proj.bias"])   # [n, hid]
+            if temb_in_gc2:
+                w2 = sd[f"{g}.gconv2.gconv.weight"][:, 0]                                                      # [3, hid, hid]
+                rows = torch.stack([torch.ones(adj.shape[0]), t1.sum(1), t2.sum(1)])                             # [3, joints]
+                tau = torch.einsum("kj,nc,kcd->njd", rows, tp, w2)
+            else:
+                h1 = h1 + tp[:, None, :]
+        h2 = torch.relu(cheb_tc(r16(h1), sd[f"{g}.gconv2.gconv.weight"], sd[f"{g}.gconv2.gconv.bias"]) + tau)
         X = X + h2
     return O.cheb_conv(X, adj, sd["gconv_output.weight"], sd["gconv_output.bias"])

@@ -19,7 +19,7 @@ def dev():
     return torch.device("cuda:0")
 
 
-EMU = {"tc": E.gcndiff_forward_tc, "tcg": lambda *a: E.gcndiff_forward_tcg(*a, p16=True)}
+EMU = {"tc": E.gcndiff_forward_tc, "tcg": lambda *a: E.gcndiff_forward_tcg(*a, p16=True, temb_in_gc2=True)}   # the sampler's form
 ENGINE_ID = {"tc": 2, "tcg": 3}
 
 
@@ -165,7 +165,7 @@ def test_tcg_other_depths(n_layer):
     g = torch.Generator().manual_seed(19)
     noise = torch.randn(3, 40, 17, 5, generator=g)
     ref = O.ddim_sample(x, None, seq, lambda a, m, tt: O.gcndiff_forward(sd, adj, n_layer, 4, a, m, tt), betas(), eta=1.0, noise=noise)[0][-1]
-    emu = O.ddim_sample(x, None, seq, lambda a, m, tt: E.gcndiff_forward_tcg(sd, adj, n_layer, 4, a, m, tt, p16=True), betas(), eta=1.0, noise=noise)[0][-1]
+    emu = O.ddim_sample(x, None, seq, lambda a, m, tt: E.gcndiff_forward_tcg(sd, adj, n_layer, 4, a, m, tt, p16=True, temb_in_gc2=True), betas(), eta=1.0, noise=noise)[0][-1]
     out = D.generalized_steps(x.to(dev()), None, seq, model, betas(), eta=1.0, noise=noise.to(dev()))[0][-1].cpu()
     amp = (emu - ref).abs().max().item()
     assert (out - emu).abs().max().item() < max(1e-4, amp)
