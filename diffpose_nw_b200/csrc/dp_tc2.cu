@@ -77,6 +77,8 @@ constexpr uint32_t COL_S0 = 96;      // attention: scores of the even head of a 
 constexpr uint32_t COL_S1 = 224;     //   overwrite the first 64 columns as packed fp16 (A operand of P V); odd head
 constexpr uint32_t COL_O = 352;      // attention output [128 x 96] (+8 scratch columns); before that the V accumulator
 constexpr uint32_t COL_ACC2 = 288;   // third accumulator group: GEMMs that start while groups 0/1 are still being read
+constexpr uint32_t COL_TA0 = 448;    // fp16 A operands kept in tensor memory (48 columns = 96 channels each): operands that
+constexpr uint32_t COL_TA1 = 384;    //   only ever feed a GEMM as A skip shared memory (its bandwidth bounds the epilogues)
 
 // shared memory map (bytes)
 constexpr int al16(int x) { return (x + 15) / 16 * 16; }
@@ -201,6 +203,21 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
     *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
     if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
   }
+}
+
+// The same for an operand that is only ever the A side of a GEMM: fp16 pairs into 24 tensor-memory columns (TS-form MMA).
+// No shared-memory store, no generic->async proxy fence.
+__device__ DP_PHASE_FN void epi_tmem(uint32_t dcol, uint32_t col, float scale, bool scaled, bool relu) {
+  float v[48];
+  tmem_ld48(col, v);
+  if (scaled) {
+#pragma unroll
+    for (int i = 0; i < 48; i += 2) mul2(v[i], v[i + 1], v[i], v[i + 1], scale, scale);
+  }
+  uint32_t pk[24];
+#pragma unroll
+  for (int i = 0; i < 24; ++i) pk[i] = relu ? pack2_relu(v[2 * i], v[2 * i + 1]) : pack2(v[2 * i], v[2 * i + 1]);
+  tmem_st24_u32(dcol, pk);
 }
 
 // LayerNorm phase: residual row (48 of its 96 channels per thread) from TMEM -> LayerNorm -> fp16 operand block
@@ -477,6 +494,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         a_lo += 2 * A_LBO >> 4; b_lo += 2 * W_LBO >> 4; acc = 1u;
       }
     };
+    // the same with A in tensor memory (48 columns of fp16 pairs from acol)
+    auto gemm_ts = [&](uint32_t wa, uint32_t acol, uint32_t dcol, uint32_t accumulate) {
+      uint32_t b_lo = desc_lo(wa, W_LBO), acc = accumulate;
+#pragma unroll 2
+      for (int ks = 0; ks < 6; ++ks) {
+        umma_ts(tb + dcol, tb + acol + 8 * ks, b_lo, kHiK, kN96, acc, leader);
+        b_lo += 2 * W_LBO >> 4; acc = 1u;
+      }
+    };
     auto bias = [&](uint32_t wa, uint32_t dcol) {
       umma_ss(tb + dcol, ones_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
     };
@@ -598,9 +624,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             if (conv == 1 && tau_step) umma_ss(tb + COL_ACC2, cs_lo, kHiK, desc_lo(sbase + OFF_PAR + ips * PAR_BYTES + LP_BYTES, 0), kHiK, kN96, 1u, leader);
             w_release();
             wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-            wait_rdy(); gemm(wa, 1, COL_ACC2, 1u); w_release();
+            wait_rdy(); gemm_ts(wa, COL_TA0, COL_ACC2, 1u); w_release();
             wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-            wait_rdy(); gemm(wa, 2, COL_ACC2, 1u); w_release();
+            wait_rdy(); gemm_ts(wa, COL_TA1, COL_ACC2, 1u); w_release();
             commit_acc();
           }
           if (++ips == 2) { ips = 0; ipphase ^= 1; }
@@ -724,6 +750,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           uint8_t* const blk2 = blk0 + 2 * ABLK_BYTES;
           const float ninf = -INFINITY;
           const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48, ocol = c.tmem_lane + COL_O + hh * 48;
+          const uint32_t ta0 = c.tmem_lane + COL_TA0 + hh * 24, ta1 = c.tmem_lane + COL_TA1 + hh * 24;   // this thread's half of a TMEM operand
           // temb added after GC1 (gcndiff.py:51).  Sampler: the issuer adds it to GC2 as a bias block, nothing to do here.
           // Forward call: one row per pose, added in the epilogue.  GCNpose: none.
           const bool pose_temb = a.forward_only && a.has_temb;
@@ -763,18 +790,18 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           // ======== x = x + GC2(GC1(x) + temb)
           epi_run(blk0, xcol, ninf, nullptr, 1.0f, false, side0);
           signal_ready(c);                                           // x as an operand -> [T1 x | T2 x] and x Wc1_0
-          wait_acc(c); epi_run(blk1, acol, ninf, nullptr, t1scale, true);
-          signal_ready(c);                                           // T1 x
-          wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
-          signal_ready(c);                                           // T2 x
+          wait_acc(c); epi_tmem(ta0, acol, t1scale, true, false);
+          signal_ready_tmem(c);                                      // T1 x
+          wait_acc(c); epi_tmem(ta1, acol + 96, t2scale, true, false);
+          signal_ready_tmem(c);                                      // T2 x
           wait_acc(c);
           if (pose_temb) epi_run(blk0, acol2, 0.f, temb_row, 1.0f, false, side0);
           else epi_run(blk0, acol2, 0.f, nullptr, 1.0f, false, side0, true);
           signal_ready(c);                                           // h = relu(GC1) (+ temb) -> [T1 h | T2 h] and h Wc2_0
-          wait_acc(c); epi_run(blk1, acol, ninf, nullptr, t1scale, true);
-          signal_ready(c);
-          wait_acc(c); epi_run(blk2, acol + 96, ninf, nullptr, t2scale, true);
-          signal_ready(c);
+          wait_acc(c); epi_tmem(ta0, acol, t1scale, true, false);
+          signal_ready_tmem(c);
+          wait_acc(c); epi_tmem(ta1, acol + 96, t2scale, true, false);
+          signal_ready_tmem(c);
           const uint32_t ps_done = ps;
           if (++ps == 2) { ps = 0; pphase ^= 1; }
           if (l + 1 < L) mbar_wait(pfull0 + 8 * ps, pphase);        // the next layer's parameters, while the last GEMM runs
