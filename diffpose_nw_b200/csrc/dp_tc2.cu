@@ -223,7 +223,8 @@ __device__ DP_PHASE_FN void epi_tmem(uint32_t dcol, uint32_t col, float scale, b
 // LayerNorm phase: residual row (48 of its 96 channels per thread) from TMEM -> LayerNorm -> fp16 operand block
 // With acol != 0 the closing residual of the previous layer's Chebyshev block is applied first: x += relu(acc), written
 // back to TMEM (later MMAs accumulate onto it).
-__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, uint32_t dst_off, uint8_t* side = nullptr) {
+__device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, int row, int hh, uint32_t dst_off, uint8_t* side = nullptr,
+                                   uint32_t tdst = 0) {
   float v[48];
   if (acol != 0) {
     float u[48];
@@ -265,6 +266,13 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   const float shift = -mean * inv;
 #pragma unroll
   for (int i = 0; i < 48; i += 2) fma2(v[i], v[i + 1], v[i], v[i + 1], inv, inv, shift, shift);
+  if (tdst != 0) {     // the operand only feeds GEMMs as A: keep it in tensor memory (the wait inside covers the residual store too)
+    uint32_t pk[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) pk[i] = pack2(v[2 * i], v[2 * i + 1]);
+    tmem_st24_u32(tdst, pk);
+    return;
+  }
   uint8_t* dst = smem + dst_off;
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -573,11 +581,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           // the next "accumulator ready" event; both sides walk the same static sequence.  Accumulator groups: ACC+0,
           // ACC+96 (also the two score regions), ACC2 and the O region, arranged so that a GEMM may start while the
           // compute warps are still reading the groups of the previous one.
-          // 1. q, k, v = LN0(x) W + b                         A = block 2; one event per output block
+          // 1. q, k, v = LN0(x) W + b                         A = TA0 (tensor memory); one event per output block
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-          wait_rdy(); gemm(wa, 2, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
-          wa = w_acquire(); gemm(wa, 2, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
-          wa = w_acquire(); gemm(wa, 2, COL_O, 0u); bias(wa, COL_O); w_release(); commit_acc();
+          wait_rdy(); gemm_ts(wa, COL_TA0, COL_ACC, 0u); bias(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire(); gemm_ts(wa, COL_TA0, COL_ACC + 96, 0u); bias(wa, COL_ACC + 96); w_release(); commit_acc();
+          wa = w_acquire(); gemm_ts(wa, COL_TA0, COL_O, 0u); bias(wa, COL_O); w_release(); commit_acc();
           // 1b. attention, two heads at a time: S = Q_h K_h^T (d_k = 24 = K step of 16 + 8 real | 8 zero columns),
           //     softmax on the compute warps (P back into TMEM), O_h = P V_h with V as an MN-major operand
           wait_rdy();                                             // q, k in blocks 0, 1
@@ -591,23 +599,23 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_rdy();                                             // P of heads 2, 3
           pv_head(2, COL_S0); pv_head(3, COL_S1);
           commit_acc();
-          // 2. x += attn Wo + bo                              A = block 0
+          // 2. x += attn Wo + bo                              A = TA0
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-          wait_rdy(); gemm(wa, 0, COL_X, 1u); bias(wa, COL_X); w_release();
+          wait_rdy(); gemm_ts(wa, COL_TA0, COL_X, 1u); bias(wa, COL_X); w_release();
           commit_acc();
           // 3. g1 = L^ LN1(x)                                 B = block 0
           wait_rdy();
           aggregate(2, 0, COL_ACC, 0u);
           commit_acc();
-          // 4. h = g1 W1 + b1 (192 outputs)                   A = block 1; one event per half
+          // 4. h = g1 W1 + b1 (192 outputs)                   A = TA0; one event per half
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-          wait_rdy(); gemm(wa, 1, COL_ACC, 0u); bias_joint(wa, COL_ACC); w_release(); commit_acc();
-          wa = w_acquire(); gemm(wa, 1, COL_ACC + 96, 0u); bias_joint(wa, COL_ACC + 96); w_release(); commit_acc();
-          // 5. z = relu(h) W2 ; x += b2                       A = blocks 0, 2, each as soon as its half of h is there
+          wait_rdy(); gemm_ts(wa, COL_TA0, COL_ACC, 0u); bias_joint(wa, COL_ACC); w_release(); commit_acc();
+          wa = w_acquire(); gemm_ts(wa, COL_TA0, COL_ACC + 96, 0u); bias_joint(wa, COL_ACC + 96); w_release(); commit_acc();
+          // 5. z = relu(h) W2 ; x += b2                       A = TA1, TA0, each as soon as its half of h is there
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-          wait_rdy(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_X); w_release();
+          wait_rdy(); gemm_ts(wa, COL_TA1, COL_ACC2, 0u); bias(wa, COL_X); w_release();
           wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-          wait_rdy(); gemm(wa, 2, COL_ACC2, 1u); w_release();
+          wait_rdy(); gemm_ts(wa, COL_TA0, COL_ACC2, 1u); w_release();
           commit_acc();
           // 6. x += L^ z                                      B = block 1
           wait_rdy();
@@ -756,12 +764,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           const bool pose_temb = a.forward_only && a.has_temb;
           const float* temb_row = reinterpret_cast<const float*>(smem + OFF_TEP) + min(row / PS, TP - 1) * H + hh * 48;
           // ======== x = x + attn(LN0(x))   (first the closing residual of the previous layer's Chebyshev block)
-          ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, my_chunk + 2 * ABLK_BYTES);
-          signal_ready(c);                                           // LN0(x) in block 2
+          ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, 0u, nullptr, ta0);
+          signal_ready_tmem(c);                                      // LN0(x) in TA0
           wait_acc(c); epi_run(blk0, acol, ninf, nullptr);           // q
           wait_acc(c); epi_run(blk1, acol + 96, ninf, nullptr);      // k
           signal_ready(c);                                           // q, k ready -> scores of heads 0, 1
-          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr, 1.0f, false, side2);   // v (block 2 = LN0(x) is no longer needed)
+          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr, 1.0f, false, side2);   // v
           signal_ready(c);                                           // v ready
           wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
@@ -770,19 +778,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
           signal_ready_tmem(c);                                      // -> P V of heads 2, 3
           wait_acc(c);
-          epi_run(blk0, ocol, ninf, nullptr);
-          signal_ready(c);                                           // -> out projection (accumulates into x)
+          epi_tmem(ta0, ocol, 1.0f, false, false);
+          signal_ready_tmem(c);                                      // -> out projection (accumulates into x)
           wait_acc(c);
           // ======== x = x + GraphNet(LN1(x))
           ln_run(smem, xcol, 0u, row, hh, my_chunk, side0);
           signal_ready(c);                                           // -> L^ y
           wait_acc(c);
-          epi_run(blk1, acol, ninf, nullptr);
-          signal_ready(c);                                           // -> fc1
-          wait_acc(c); epi_run(blk0, acol, 0.f, nullptr, 1.0f, false, nullptr, true);
-          signal_ready(c);                                           // first half of relu(h) -> fc2, first K block
-          wait_acc(c); epi_run(blk2, acol + 96, 0.f, nullptr, 1.0f, false, nullptr, true);
-          signal_ready(c);                                           // second half
+          epi_tmem(ta0, acol, 1.0f, false, false);
+          signal_ready_tmem(c);                                      // -> fc1
+          wait_acc(c); epi_tmem(ta1, acol, 1.0f, false, true);
+          signal_ready_tmem(c);                                      // first half of relu(h) -> fc2, first K block
+          wait_acc(c); epi_tmem(ta0, acol + 96, 1.0f, false, true);  // (fc1 has finished reading TA0)
+          signal_ready_tmem(c);                                      // second half
           wait_acc(c);
           epi_run(blk1, acol2, ninf, nullptr, 1.0f, false, side1);
           signal_ready(c);                                           // -> L^ z (accumulates into x)
