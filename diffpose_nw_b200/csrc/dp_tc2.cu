@@ -178,7 +178,7 @@ __device__ __forceinline__ void wait_acc_t(Ctx& c) {
 // side: for the joint-16 row of a pose, where its chunks go in the block's side buffer (nullptr for every other row and
 // for blocks that are never aggregated)
 __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false,
-                                    uint8_t* side = nullptr, bool relu_in_cvt = false) {
+                                    uint8_t* side = nullptr, bool relu_in_cvt = false, bool b_only = false) {
   float v[48];
   tmem_ld48(col, v);
   if (scaled) {              // row scale of an integerised graph matrix
@@ -196,6 +196,15 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
       add2(v[i], v[i + 1], v[i], v[i + 1], t.x, t.y);
       add2(v[i + 2], v[i + 3], v[i + 2], v[i + 3], t.z, t.w);
     }
+  }
+  if (b_only) {
+    // the block is only ever read as a B operand (per-pose windows over joints 0..15 + the side buffer): a joint-16 row goes
+    // to the side buffer alone -- one store per chunk instead of two (the phase is bound by shared-memory store issue)
+    uint8_t* const d = side != nullptr ? side : dst;
+    const int stride = side != nullptr ? SIDE_LBO : A_LBO;
+#pragma unroll
+    for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(d + q * stride) = relu_in_cvt ? pack8_relu(v + 8 * q) : pack8(v + 8 * q);
+    return;
   }
 #pragma unroll
   for (int q = 0; q < 6; ++q) {
@@ -273,13 +282,11 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
     tmem_st24_u32(tdst, pk);
     return;
   }
-  uint8_t* dst = smem + dst_off;
+  // shared-memory destination: a B operand (LN1 -> L^ aggregation); joint-16 rows go to the side buffer only (see epi_run)
+  uint8_t* const d = side != nullptr ? side : smem + dst_off;
+  const int stride = side != nullptr ? SIDE_LBO : A_LBO;
 #pragma unroll
-  for (int q = 0; q < 6; ++q) {
-    const uint4 u = pack8(v + 8 * q);
-    *reinterpret_cast<uint4*>(dst + q * A_LBO) = u;
-    if (side != nullptr) *reinterpret_cast<uint4*>(side + q * SIDE_LBO) = u;
-  }
+  for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(d + q * stride) = pack8(v + 8 * q);
   if (acol != 0) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
@@ -769,7 +776,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_run(blk0, acol, ninf, nullptr);           // q
           wait_acc(c); epi_run(blk1, acol + 96, ninf, nullptr);      // k
           signal_ready(c);                                           // q, k ready -> scores of heads 0, 1
-          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr, 1.0f, false, side2);   // v
+          wait_acc(c); epi_run(blk2, ocol, ninf, nullptr, 1.0f, false, side2, false, true);   // v
           signal_ready(c);                                           // v ready
           wait_acc(c);
           softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
@@ -792,7 +799,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_tmem(ta0, acol + 96, 1.0f, false, true);  // (fc1 has finished reading TA0)
           signal_ready_tmem(c);                                      // second half
           wait_acc(c);
-          epi_run(blk1, acol2, ninf, nullptr, 1.0f, false, side1);
+          epi_run(blk1, acol2, ninf, nullptr, 1.0f, false, side1, false, true);
           signal_ready(c);                                           // -> L^ z (accumulates into x)
           wait_acc(c);
           // ======== x = x + GC2(GC1(x) + temb)
