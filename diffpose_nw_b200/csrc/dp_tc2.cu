@@ -178,7 +178,7 @@ __device__ __forceinline__ void wait_acc_t(Ctx& c) {
 // side: for the joint-16 row of a pose, where its chunks go in the block's side buffer (nullptr for every other row and
 // for blocks that are never aggregated)
 __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const float* temb, float scale = 1.0f, bool scaled = false,
-                                    uint8_t* side = nullptr, bool relu_in_cvt = false, bool b_only = false) {
+                                    uint8_t* side = nullptr, bool relu_in_cvt = false, bool b_only = false, uint32_t tdst = 0) {
   float v[48];
   tmem_ld48(col, v);
   if (scaled) {              // row scale of an integerised graph matrix
@@ -198,12 +198,17 @@ __device__ DP_PHASE_FN void epi_run(uint8_t* dst, uint32_t col, float lo, const 
     }
   }
   if (b_only) {
-    // the block is only ever read as a B operand (per-pose windows over joints 0..15 + the side buffer): a joint-16 row goes
-    // to the side buffer alone -- one store per chunk instead of two (the phase is bound by shared-memory store issue)
+    // the shared-memory copy is only ever read as a B operand (per-pose windows over joints 0..15 + the side buffer): a
+    // joint-16 row goes to the side buffer alone -- one store per chunk instead of two (the phase is bound by shared-memory
+    // store issue).  tdst: the same operand is also the A side of a GEMM -> second copy in tensor memory.
     uint8_t* const d = side != nullptr ? side : dst;
     const int stride = side != nullptr ? SIDE_LBO : A_LBO;
+    uint32_t pk[24];
 #pragma unroll
-    for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(d + q * stride) = relu_in_cvt ? pack8_relu(v + 8 * q) : pack8(v + 8 * q);
+    for (int i = 0; i < 24; ++i) pk[i] = relu_in_cvt ? pack2_relu(v[2 * i], v[2 * i + 1]) : pack2(v[2 * i], v[2 * i + 1]);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) *reinterpret_cast<uint4*>(d + q * stride) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+    if (tdst != 0) tmem_st24_u32(tdst, pk);
     return;
   }
 #pragma unroll
@@ -518,6 +523,16 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         b_lo += 2 * W_LBO >> 4; acc = 1u;
       }
     };
+    // A converted in place inside its own fp32 accumulator [abase, abase+96): each half of the columns holds the 24 fp16
+    // pairs of its own 48 channels (the two threads of a row convert their halves independently)
+    auto gemm_ts_inplace = [&](uint32_t wa, uint32_t abase, uint32_t dcol, uint32_t accumulate) {
+      uint32_t b_lo = desc_lo(wa, W_LBO), acc = accumulate;
+#pragma unroll 2
+      for (int ks = 0; ks < 6; ++ks) {
+        umma_ts(tb + dcol, tb + abase + 8 * ks + (ks >= 3 ? 24 : 0), b_lo, kHiK, kN96, acc, leader);
+        b_lo += 2 * W_LBO >> 4; acc = 1u;
+      }
+    };
     auto bias = [&](uint32_t wa, uint32_t dcol) {
       umma_ss(tb + dcol, ones_lo, kHiK, desc_lo(wa + 12 * W_LBO, W_LBO), kHiK, kN96, 1u, leader);
     };
@@ -635,13 +650,13 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             wait_rdy();
             aggregate(0, 0, COL_ACC, 0u); commit_acc();
             aggregate(1, 0, COL_ACC + 96, 0u); commit_acc();
-            wa = w_acquire(); gemm(wa, 0, COL_ACC2, 0u); bias(wa, COL_ACC2);
+            wa = w_acquire(); gemm_ts(wa, conv == 0 ? COL_TA0 : COL_TA1, COL_ACC2, 0u); bias(wa, COL_ACC2);
             if (conv == 1 && tau_step) umma_ss(tb + COL_ACC2, cs_lo, kHiK, desc_lo(sbase + OFF_PAR + ips * PAR_BYTES + LP_BYTES, 0), kHiK, kN96, 1u, leader);
             w_release();
             wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-            wait_rdy(); gemm_ts(wa, COL_TA0, COL_ACC2, 1u); w_release();
+            wait_rdy(); gemm_ts_inplace(wa, COL_ACC, COL_ACC2, 1u); w_release();
             wa = w_acquire();     // (before the wait: the weights are there long before the operands)
-            wait_rdy(); gemm_ts(wa, COL_TA1, COL_ACC2, 1u); w_release();
+            wait_rdy(); gemm_ts_inplace(wa, COL_ACC + 96, COL_ACC2, 1u); w_release();
             commit_acc();
           }
           if (++ips == 2) { ips = 0; ipphase ^= 1; }
@@ -803,19 +818,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);                                           // -> L^ z (accumulates into x)
           wait_acc(c);
           // ======== x = x + GC2(GC1(x) + temb)
-          epi_run(blk0, xcol, ninf, nullptr, 1.0f, false, side0);
-          signal_ready(c);                                           // x as an operand -> [T1 x | T2 x] and x Wc1_0
-          wait_acc(c); epi_tmem(ta0, acol, t1scale, true, false);
-          signal_ready_tmem(c);                                      // T1 x
-          wait_acc(c); epi_tmem(ta1, acol + 96, t2scale, true, false);
-          signal_ready_tmem(c);                                      // T2 x
-          wait_acc(c);
-          if (pose_temb) epi_run(blk0, acol2, 0.f, temb_row, 1.0f, false, side0);
-          else epi_run(blk0, acol2, 0.f, nullptr, 1.0f, false, side0, true);
-          signal_ready(c);                                           // h = relu(GC1) (+ temb) -> [T1 h | T2 h] and h Wc2_0
-          wait_acc(c); epi_tmem(ta0, acol, t1scale, true, false);
+          epi_run(blk0, xcol, ninf, nullptr, 1.0f, false, side0, false, true, ta0);
+          signal_ready(c);                                           // x as an operand: B (block 0) -> [T1 x | T2 x], A (TA0) -> x Wc1_0
+          wait_acc(c); epi_tmem(acol, acol, t1scale, true, false);   // T1 x, converted in place
           signal_ready_tmem(c);
-          wait_acc(c); epi_tmem(ta1, acol + 96, t2scale, true, false);
+          wait_acc(c); epi_tmem(acol + 96, acol + 96, t2scale, true, false);   // T2 x
+          signal_ready_tmem(c);
+          wait_acc(c);
+          if (pose_temb) epi_run(blk0, acol2, 0.f, temb_row, 1.0f, false, side0, false, true, ta1);
+          else epi_run(blk0, acol2, 0.f, nullptr, 1.0f, false, side0, true, true, ta1);
+          signal_ready(c);                                           // h = relu(GC1) (+ temb) -> [T1 h | T2 h] and h Wc2_0
+          wait_acc(c); epi_tmem(acol, acol, t1scale, true, false);
+          signal_ready_tmem(c);
+          wait_acc(c); epi_tmem(acol + 96, acol + 96, t2scale, true, false);
           signal_ready_tmem(c);
           const uint32_t ps_done = ps;
           if (++ps == 2) { ps = 0; pphase ^= 1; }
