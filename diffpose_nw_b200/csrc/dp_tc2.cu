@@ -751,9 +751,17 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         signal_ready(c);                                           // -> 0
         mbar_wait(pfull0 + 8 * ps, pphase);                        // layer 0's parameters (checked here, off the critical path)
         wait_acc(c);
+        const uint32_t acol = c.tmem_lane + COL_ACC + hh * 48;      // this thread's half of accumulator group 0
+        const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48, ocol = c.tmem_lane + COL_O + hh * 48;
+        const uint32_t ta0 = c.tmem_lane + COL_TA0 + hh * 24, ta1 = c.tmem_lane + COL_TA1 + hh * 24;   // this thread's half of a TMEM operand
+        // The loop is rotated: LN0 of a layer runs at the end of the previous iteration (here for layer 0), so that the
+        // backward branch -- an instruction-cache miss on this part -- and the parameter copies below fall into the wait
+        // for the q GEMM instead of sitting in front of LN0 on the critical path.
+        ln_run(smem, xcol, 0u, row, hh, 0u, nullptr, ta0);
+        signal_ready_tmem(c);                                        // LN0(x) in TA0
 
         for (int l = 0; l < L; ++l) {
-          // this layer's parameters (LayerNorm gains, L^, temb) have been staged by the producer
+          // this layer's parameters (L^, joint slab, time-embedding block) have been staged by the producer
           const uint8_t* par = smem + OFF_PAR + ps * PAR_BYTES;
           if (a.forward_only && a.has_temb && tid < TP * (H / 4)) {   // per-sample timesteps: this layer's temb row of every pose
             const int p = tid / (H / 4), c4 = tid - p * (H / 4);
@@ -774,20 +782,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           // The layer is a fixed sequence of compute phases, each followed by "operands ready" and a wait for the
           // accumulators of the MMA group it feeds (the issuer runs the matching program).  Straight-line code on
           // purpose: on this part every taken branch to code that is not next in line costs an instruction-cache miss.
-          const uint32_t acol = c.tmem_lane + COL_ACC + hh * 48;    // this thread's half of accumulator group 0
           uint8_t* const blk0 = smem + my_chunk;                     // its chunks in operand blocks 0, 1, 2
           uint8_t* const blk1 = blk0 + ABLK_BYTES;
           uint8_t* const blk2 = blk0 + 2 * ABLK_BYTES;
           const float ninf = -INFINITY;
-          const uint32_t acol2 = c.tmem_lane + COL_ACC2 + hh * 48, ocol = c.tmem_lane + COL_O + hh * 48;
-          const uint32_t ta0 = c.tmem_lane + COL_TA0 + hh * 24, ta1 = c.tmem_lane + COL_TA1 + hh * 24;   // this thread's half of a TMEM operand
           // temb added after GC1 (gcndiff.py:51).  Sampler: the issuer adds it to GC2 as a bias block, nothing to do here.
           // Forward call: one row per pose, added in the epilogue.  GCNpose: none.
           const bool pose_temb = a.forward_only && a.has_temb;
           const float* temb_row = reinterpret_cast<const float*>(smem + OFF_TEP) + min(row / PS, TP - 1) * H + hh * 48;
-          // ======== x = x + attn(LN0(x))   (first the closing residual of the previous layer's Chebyshev block)
-          ln_run(smem, xcol, l > 0 ? acol2 : 0u, row, hh, 0u, nullptr, ta0);
-          signal_ready_tmem(c);                                      // LN0(x) in TA0
+          // ======== x = x + attn(LN0(x))   (LN0 has been signalled already)
           wait_acc(c); epi_run(blk0, acol, ninf, nullptr);           // q
           wait_acc(c); epi_run(blk1, acol + 96, ninf, nullptr);      // k
           signal_ready(c);                                           // q, k ready -> scores of heads 0, 1
@@ -838,6 +841,11 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c);                                               // GC2 in ACC2: the residual is applied by the next phase
           __syncwarp();
           if (lane == 0) mbar_arrive(pempty0 + 8 * ps_done);         // GC2 was the last reader of this layer's parameter stage
+          if (l + 1 < L) {
+            // closing residual of this layer's Chebyshev block, then LN0 of the next layer
+            ln_run(smem, xcol, acol2, row, hh, 0u, nullptr, ta0);
+            signal_ready_tmem(c);                                    // LN0(x) in TA0
+          }
         }
 
         // ---- output ChebConv (N = 5): U_k = X Wout_k on the tensor cores with X = hi + lo, then
