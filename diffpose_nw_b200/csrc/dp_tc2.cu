@@ -719,9 +719,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       }
       bar_compute();
 
-      for (int step = 0; step < a.n_steps; ++step) {
-        // ---- input ChebConv (ChebConv.py:74-88, K = 15): the panel [x | T1 x | T2 x | 1] of every row, split into
-        //      fp16 hi and lo parts, becomes chunk columns 0..5 of operand block 0 (hi, lo, hi)
+      // ---- input ChebConv (ChebConv.py:74-88, K = 15): the panel [x | T1 x | T2 x | 1] of every row, split into
+      //      fp16 hi and lo parts, becomes chunk columns 0..5 of operand block 0 (hi, lo, hi)
+      auto build_panel = [&]() {
         if (tid < TM) {
           const int r = tid;
           float pv[16];
@@ -748,7 +748,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           *reinterpret_cast<uint4*>(dst + a_chunk(r, 2)) = l0; *reinterpret_cast<uint4*>(dst + a_chunk(r, 3)) = l1;
           *reinterpret_cast<uint4*>(dst + a_chunk(r, 4)) = h0; *reinterpret_cast<uint4*>(dst + a_chunk(r, 5)) = h1;
         }
-        signal_ready(c);                                           // -> 0
+      };
+      build_panel();
+      signal_ready(c);                                             // -> 0 (in-conv operands of step 0)
+      for (int step = 0; step < a.n_steps; ++step) {
         mbar_wait(pfull0 + 8 * ps, pphase);                        // layer 0's parameters (checked here, off the critical path)
         wait_acc(c);
         const uint32_t acol = c.tmem_lane + COL_ACC + hh * 48;      // this thread's half of accumulator group 0
@@ -917,6 +920,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           }
         }
         bar_compute();   // scratch (= the head of operand block 0) is free again: the next panel / epilogues overwrite it
+        if (step + 1 < a.n_steps) {   // the next step's panel before the backward branch: that one then falls into the in-conv wait
+          build_panel();
+          signal_ready(c);
+        }
       }
       if (!a.forward_only) {
         for (int idx = tid; idx < nval; idx += kComputeThreads) {
