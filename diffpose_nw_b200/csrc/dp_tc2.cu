@@ -65,7 +65,6 @@ constexpr int LP_BYTES = LP_LHAT_BYTES + LP_JS_BYTES;   // 1376, copied from the
 constexpr int LP_TAU_BYTES = H * 16;                // time-embedding block of one (step, layer): [96 outputs][8] fp16 (tc2_tau_kernel)
 constexpr int PAR_BYTES = LP_BYTES + LP_TAU_BYTES;  // 2912 per stage
 constexpr int JS_BYTES = TM * 16;                   // joint slab: one chunk column [128 rows x 8]
-constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
 constexpr int kComputeThreads = 256;
 constexpr int kProducerWarp = 8, kIssuerWarp = 9;
 constexpr int kThreads = kComputeThreads + 64;
@@ -94,15 +93,14 @@ constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][XS] fp32
 constexpr int XS = 9;                                      // x_t row stride in floats: odd, so row-per-lane access is conflict free
 constexpr int OFF_PAR = al16(OFF_XT + TM * XS * 4);        // per-layer parameters, 2 stages
 constexpr int OFF_TEP = OFF_PAR + 2 * PAR_BYTES;           // per-pose temb [7][96] fp32 (forward mode: per-sample timesteps)
-constexpr int OFF_NBI = OFF_TEP + TP * H * 4;              // neighbour index  [17][9] int
-constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
-constexpr int OFF_STAT = al16(OFF_NBC + NP * NNB * 8);     // LayerNorm partial statistics [2][128] float2
+constexpr int OFF_T12 = OFF_TEP + TP * H * 4;              // (T1, T2)[17][17] as float2, fp32: the 5-wide input / output convolutions
+constexpr int OFF_STAT = al16(OFF_T12 + NP * NP * 8);      // LayerNorm partial statistics [2][128] float2
 constexpr int OFF_MASK = OFF_STAT + 2 * TM * 8;            // key mask [32]
 constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], (unused)[4], acc[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_CS % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 && OFF_XT % 16 == 0 &&
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_CS % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_T12 % 16 == 0 && OFF_XT % 16 == 0 &&
               OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && OFF_TEP % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -381,8 +379,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   const uint32_t sbase = smem_u32(smem);
   float* xt = reinterpret_cast<float*>(smem + OFF_XT);
   float* maskf = reinterpret_cast<float*>(smem + OFF_MASK);
-  int* nbi = reinterpret_cast<int*>(smem + OFF_NBI);
-  float2* nbc = reinterpret_cast<float2*>(smem + OFF_NBC);
+  float2* t12 = reinterpret_cast<float2*>(smem + OFF_T12);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
   // diagnostic stamps of CTA 0 (last four slots of the trace buffer): kernel entry, setup done, tiles done
   long long* const ktrace = (TRACE && blockIdx.x == 0 && tid == 0 && a.trace != nullptr && a.trace_cap >= 8) ? a.trace + a.trace_cap - 4 : nullptr;
@@ -433,15 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     *reinterpret_cast<uint4*>(smem + OFF_CS + tid * 16) = make_uint4(pack2(1.f, 1.f), pack2(p1h, p1h), pack2(p1 - p1h, p2h), pack2(p2h, p2 - p2h));
   }
   if (tid < 32) maskf[tid] = (tid >= 24 && tid < 24 + a.c_out) ? __ldg(w.bout + tid - 24) : ((tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f);   // [0,17) key mask, [24,29) output bias
-  if (tid < NP) {
-    // neighbour list of joint tid: columns where T1 or T2 is non-zero, padded with (self, 0, 0)
-    int n = 0;
-    for (int j = 0; j < NP; ++j) {
-      const float c1 = __ldg(w.t1 + tid * NP + j), c2 = __ldg(w.t2 + tid * NP + j);
-      if ((c1 != 0.f || c2 != 0.f) && n < NNB) { nbi[tid * NNB + n] = j; nbc[tid * NNB + n] = make_float2(c1, c2); ++n; }
-    }
-    for (; n < NNB; ++n) { nbi[tid * NNB + n] = tid; nbc[tid * NNB + n] = make_float2(0.f, 0.f); }
-  }
+  if (tid < NP * NP) t12[tid] = make_float2(__ldg(w.t1 + tid), __ldg(w.t2 + tid));
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
@@ -731,10 +720,12 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           if (p < TP && i < NP) {
 #pragma unroll
             for (int cc = 0; cc < 5; ++cc) pv[cc] = xt[r * XS + cc];
-#pragma unroll 1
-            for (int n = 0; n < NNB; ++n) {
-              const float* u = xt + (p * PS + nbi[i * NNB + n]) * XS;
-              const float2 cf = nbc[i * NNB + n];
+            // dense over the 17 joints of the pose: no index indirection, every load is independent of the others (a
+            // neighbour list would save multiplications by zero but chain two shared-memory latencies per entry)
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+              const float* u = xt + (p * PS + n) * XS;
+              const float2 cf = t12[i * NP + n];
 #pragma unroll
               for (int cc = 0; cc < 5; ++cc) { pv[5 + cc] = fmaf(cf.x, u[cc], pv[5 + cc]); pv[10 + cc] = fmaf(cf.y, u[cc], pv[10 + cc]); }
             }
@@ -895,10 +886,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             float et[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) et[k] = maskf[24 + n0 + k] + scratch[r * SCR + n0 + k];   // (slots past c_out are never stored)
-#pragma unroll 1
-            for (int q = 0; q < NNB; ++q) {
-              const float* u = scratch + (p * PS + nbi[i * NNB + q]) * SCR + n0;
-              const float2 cf = nbc[i * NNB + q];
+#pragma unroll
+            for (int q = 0; q < NP; ++q) {
+              const float* u = scratch + (p * PS + q) * SCR + n0;
+              const float2 cf = t12[i * NP + q];
 #pragma unroll
               for (int k = 0; k < 3; ++k) et[k] = fmaf(cf.y, u[10 + k], fmaf(cf.x, u[5 + k], et[k]));
             }

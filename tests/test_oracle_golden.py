@@ -83,3 +83,30 @@ def test_sampler_properties():
     # the restatement keeps that behaviour (the product returns an empty tensor instead, see test_gpu_parity)
     with pytest.raises(RuntimeError):
         O.ddim_sample(x[:0], None, [0, 12], den, betas())
+
+
+def test_tensor_core_emulation_is_an_fp16_perturbation_of_the_oracle():
+    """oracle/tc_emulation.py restates the tensor-core engine's rounding points (fp16 operands, folded LayerNorm gains,
+    time embedding inside GC2).  On CPU: it must be the oracle up to fp16-operand noise -- both forms of the time
+    embedding, masked keys and GCNpose -- and the two forms must agree with each other much better than with fp32."""
+    from oracle import tc_emulation as E
+    import diffpose_nw_b200 as D
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in D.FusedGCNdiff(adj, O.default_config()).state_dict().items()}, seed=5, scale=0.05)
+    x = O.synthetic_poses(6, seed=4)
+    tt = torch.tensor([0.0, 3.0, 12.0, 12.0, 37.0, 49.0])
+    mask = torch.ones(1, 1, 17, dtype=torch.bool)
+    mask[0, 0, 5] = mask[0, 0, 11] = False
+    for m in (None, mask):
+        ref = O.gcndiff_forward(sd, adj, 5, 4, x, m, tt)
+        add = E.gcndiff_forward_tcg(sd, adj, 5, 4, x, m, tt, p16=True)
+        fold = E.gcndiff_forward_tcg(sd, adj, 5, 4, x, m, tt, p16=True, temb_in_gc2=True)
+        scale = ref.abs().max().item()
+        assert (add - ref).abs().max().item() < 2e-3 * scale and (fold - ref).abs().max().item() < 2e-3 * scale
+        assert (add - fold).abs().max().item() < 1e-3 * scale
+    torch.manual_seed(1)
+    sdp = O.perturb_state_dict({k: v.detach().clone() for k, v in D.FusedGCNpose(adj, O.default_config(coords_dim=[2, 3])).state_dict().items()}, seed=6, scale=0.05)
+    uv = x[:, :, :2].contiguous()
+    ref = O.gcnpose_forward(sdp, adj, 5, 4, uv, None)
+    assert (E.gcnpose_forward_tcg(sdp, adj, 5, 4, uv, None) - ref).abs().max().item() < 2e-3 * ref.abs().max().item()
