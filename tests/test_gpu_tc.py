@@ -172,6 +172,31 @@ def test_tcg_other_depths(n_layer):
     assert (out - ref).abs().max().item() < 1e-3
 
 
+def test_tcg_denser_graph():
+    """Nothing in the engine is specific to the H36M tree: a hub joined to every joint makes every row of T2 dense (the
+    5-wide input / output convolutions read a dense (T1, T2) table, the Chebyshev slab carries whatever the row sums
+    are, the integerised rows fall back to fp16 where no common denominator exists).  Against the fp32 oracle and the
+    fp32 engine."""
+    edges = list(D.H36M_EDGES) + [(0, j) for j in range(1, 17)]
+    adj = D.adj_mx_from_edges(17, edges)
+    assert ((O.cheb_basis(adj)[2] != 0).sum(1) > 9).any()
+    torch.manual_seed(3)
+    model = D.FusedGCNdiff(adj, O.default_config())
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, seed=14)
+    model.load_state_dict(sd)
+    model = model.to(dev())
+    x = O.synthetic_poses(30, seed=18)
+    seq = [0, 12]
+    g = torch.Generator().manual_seed(20)
+    noise = torch.randn(2, 30, 17, 5, generator=g)
+    ref = O.ddim_sample(x, None, seq, lambda a, m, tt: O.gcndiff_forward(sd, adj, 5, 4, a, m, tt), betas(), eta=1.0, noise=noise)[0][-1]
+    out = D.generalized_steps(x.to(dev()), None, seq, model, betas(), eta=1.0, noise=noise.to(dev()))[0][-1].cpu()
+    assert model.last_launch()[4] == ENGINE_ID["tcg"]
+    assert (out - ref).abs().max().item() < 1e-3
+    out32 = D.generalized_steps(x.to(dev()), None, seq, model.set_engine("fp32"), betas(), eta=1.0, noise=noise.to(dev()))[0][-1].cpu()
+    assert (out32 - ref).abs().max().item() < 2e-5
+
+
 def test_tcg_long_schedule_steps_on_device():
     """More than 64 DDIM steps: the step scalars no longer travel by value but through a device array."""
     cfg = O.default_config()
