@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_POSE_FORWARD = 24.65e6          # minimal algorithmic work, SURVEY.md section 8d
 ROW_BYTES = 17 * 5 * 4                   # one uvxyz pose, fp32
-NCU_DRAM_BYTES_PER_LAUNCH = 2036480      # configs[1], tc2_kernel: 2.04 MB read (weights + poses), 0 B written back (stays in L2)
+NCU_DRAM_BYTES_PER_LAUNCH = 2033152      # configs[1], tc2_kernel: 2.03 MB read (weights + poses), 0 B written back (stays in L2)
 METRIC = "poses/sec, full DDIM sampling (H hyps x T steps)"
 
 WORKLOADS = {
@@ -277,11 +277,20 @@ def main():
     host_in = [torch.empty(B, 17, 5).pin_memory() for _ in range(2)]
     host_in[0].copy_(base); host_in[1].copy_(base)
     out_rows = B if H > 1 else B * H
-    hs = D.HostStream(model, batch=B, seq=seq, betas=betas, eta=eta, test_times=H) if noise is None else None    # (two-stage: times the refinement stage)
+    two_stage = pose_model is not None
+    hs = D.HostStream(model, batch=B, seq=seq, betas=betas, eta=eta, test_times=H) if (noise is None and not two_stage) else None
     xd = torch.empty(B, 17, 5, device=dev)
+    if two_stage:       # the two-stage pipeline takes 2D keypoints from the host: [B,17,2] in, refined [B,17,5] out
+        host_uv = [base[:, :, :2].contiguous().pin_memory() for _ in range(2)]
+        uvd = torch.empty(B, 17, 2, device=dev)
     host_out = [torch.empty(out_rows, 17, 5).pin_memory() for _ in range(2)]
 
     def e2e_serial(i):      # eta > 0 with device noise: plain copy -> sample -> copy (HostStream draws no noise itself)
+        if two_stage:
+            uvd.copy_(host_uv[i & 1], non_blocking=True)
+            o = D.lift_and_refine(model, model_pose=pose_model, input_2d=uvd, src_mask=None, seq=seq, betas=betas, eta=eta, test_times=H)
+            host_out[i & 1].copy_(o, non_blocking=True)
+            return
         xd.copy_(host_in[i & 1], non_blocking=True)
         o = D.sample(model, xd, None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=(H > 1), steps=steps_arr)
         host_out[i & 1].copy_(o, non_blocking=True)
@@ -333,12 +342,12 @@ def main():
                        "l2": f"inputs rotate through a {pool_n * batch_bytes / 2**20:.0f} MiB pool (> 126 MiB L2) when steps+warmup >= {pool_n}; "
                              "weights stay L2-resident by design",
                        "launch": {"grid": ll[0], "block": ll[1], "smem": ll[2], "poses_per_tile": ll[3], "tiles": ll[5]}},
-            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": B * ROW_BYTES, "d2h_bytes_per_step": out_rows * ROW_BYTES,
-                    "steps": e_steps, "ms_per_step": e_ms / e_steps},
+            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": B * 17 * 2 * 4 if two_stage else B * ROW_BYTES,
+                    "d2h_bytes_per_step": out_rows * ROW_BYTES, "steps": e_steps, "ms_per_step": e_ms / e_steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.workload == "cpn1024" and model.engine() == "tcg") else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per tc2_kernel launch (profiles/r01c_ncu_tcg_metrics.csv)",
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per tc2_kernel launch (profiles/r01e_ncu_tcg_metrics.csv)",
                          "peak_source": peaks["src"],
                          "note": "achieved = 24.65 MFLOP x poses x H x T per dp_sample / mean device time of dp_sample (temb prologue + persistent kernel)",
                          "hbm_gbs": hbm_bytes / per_launch_s / 1e9},

@@ -144,6 +144,12 @@ __device__ __forceinline__ void tmem_st24_u32(uint32_t taddr, const uint32_t* p)
   asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
 
+// 1/x to 1 ulp (MUFU.RCP alone): the consumers round to fp16 right after
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));

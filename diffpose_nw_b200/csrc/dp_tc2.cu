@@ -272,7 +272,7 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
   const float m2 = fmaxf(fmaf(-(sh + o.x), mean, qh + o.y), 0.f);          // sum (x - mean)^2
   float sd;
   asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(sd) : "f"(m2 * (1.0f / (float)(H - 1))));
-  const float inv = __frcp_rn(sd + 1e-6f);
+  const float inv = rcp_fast(sd + 1e-6f);
   // (x - mean) / (std + eps): the gains a_2, b_2 are folded into the weights and biases of the GEMMs that consume this
   // operand (tc2_pack), so nothing is read from shared memory here -- the phase is bound by shared-memory bandwidth
   const float shift = -mean * inv;
@@ -334,7 +334,7 @@ __device__ DP_PHASE_FN void softmax_run(const uint8_t* smem, uint32_t region, in
     add2(s2, s3, s2, s3, sc[j + 2], sc[j + 3]);
   }
   sc[16] = ex2(fmaf(sc[16], k2, nmk));
-  const float inv = __frcp_rn((s0 + s1) + (s2 + s3) + sc[16]);
+  const float inv = rcp_fast((s0 + s1) + (s2 + s3) + sc[16]);
 #pragma unroll
   for (int j = 0; j < 16; j += 2) mul2(sc[j], sc[j + 1], sc[j], sc[j + 1], inv, inv);
   sc[16] *= inv;
