@@ -2,7 +2,12 @@
 // CTA, all DDIM steps and layers executed without leaving the SM.  Every contraction of the denoiser runs on tcgen05:
 //
 //   * dense projections (QKV, out-proj, GraphNet fc1/fc2, Chebyshev convolutions) as M=128, N=96, K=16 fp16 MMAs with
-//     fp32 accumulators in TMEM; biases ride along as one extra K step against a constant-one slab;
+//     fp32 accumulators in TMEM; biases ride along as one extra K step against a constant-one slab.  An activation
+//     that is only ever the A side of a GEMM never touches shared memory: the epilogue writes it as packed fp16 pairs
+//     into tensor memory (TS-form MMA); only B operands (K, V, LN1(x), z, x, h) and Q live in shared memory;
+//   * LayerNorm writes the plain normalised row: the gains are folded into the consumer's weights and bias at pack
+//     time (for LN1, whose output first goes through L^, the shift enters through a per-joint K slab); the sampler's
+//     time embedding enters GC2 as one more bias K step (Chebyshev slab x per-(step, layer) block);
 //   * the residual stream X lives in TMEM (96 fp32 columns).  Residual additions are free: the out-projection, the
 //     second GraphNet aggregation and the b2 bias accumulate straight into those columns (D += A*B);
 //   * the 17x17 graph operators (Chebyshev T1/T2, learnable-adjacency L^).  Joints 0..15: a graph matrix G is stored
@@ -17,8 +22,8 @@
 //   * the input (K = 15) and output (N = 15) Chebyshev convolutions with hi/lo fp16 splits of both operands (three
 //     MMAs per product), i.e. at fp32-level accuracy.
 //
-// Warp roles: 8 compute warps (epilogues TMEM -> registers -> fp16 operand in shared memory, LayerNorm, softmax, DDIM
-// update), one producer warp (weights and per-layer parameters L2 -> shared memory with cp.async.bulk + mbarrier
+// Warp roles: 8 compute warps (epilogues TMEM -> registers -> fp16 operand in tensor or shared memory, LayerNorm,
+// softmax, DDIM update), one producer warp (weights and per-layer parameters L2 -> shared memory with cp.async.bulk + mbarrier
 // complete_tx, 4-stage ring of 21.5 KB blocks), one issuer warp (every tcgen05.mma, following a static per-layer
 // program).  Compute warps and issuer hand over through two 4-deep event rings, both sides walking the same static
 // sequence: "operands ready" = hardware named barriers (bar.arrive by the 256 compute threads, bar.sync by the issuer warp:
@@ -474,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     // ---------------------------------------------------------------- MMA issuer: the whole warp runs the static program
     // (every value is warp-uniform), one elected lane issues
     const uint32_t leader = elect_one() ? 1u : 0u;
-    uint32_t stage = 0, phase = 0, rdy_i = 0, rdy_phase = 0, acc_i = 0;
+    uint32_t stage = 0, phase = 0, rdy_i = 0, acc_i = 0;
     long long* itrace = (TRACE && blockIdx.x == 0 && a.trace != nullptr && leader) ? a.trace + a.trace_cap / 2 : nullptr;   // issuer stamps: second half
     int itrace_n = 0;
     auto imark = [&]() { if (TRACE && itrace != nullptr && itrace_n < a.trace_cap / 2) itrace[itrace_n++] = clock64(); };
@@ -494,16 +499,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     constexpr uint32_t kHiActMn = desc_hi(A_LBO);    // activations as MN-major B: 8-channel groups one chunk column apart
     constexpr uint32_t kN96 = idesc_f16(96, false), kN96Mn = idesc_f16(96, true), kN128 = idesc_f16(128, false), kN32Mn = idesc_f16(32, true),
                        kN16 = idesc_f16(16, false);
-    // D[:, dcol..dcol+96) (+)= block a_blk [128 x 96] * W^T
-    auto gemm = [&](uint32_t wa, int a_blk, uint32_t dcol, uint32_t accumulate) {
-      uint32_t a_lo = desc_lo(sbase + OFF_A + a_blk * ABLK_BYTES, A_LBO), b_lo = desc_lo(wa, W_LBO), acc = accumulate;
-#pragma unroll 2
-      for (int ks = 0; ks < 6; ++ks) {
-        umma_ss(tb + dcol, a_lo, kHiK, b_lo, kHiK, kN96, acc, leader);
-        a_lo += 2 * A_LBO >> 4; b_lo += 2 * W_LBO >> 4; acc = 1u;
-      }
-    };
-    // the same with A in tensor memory (48 columns of fp16 pairs from acol)
+    // D[:, dcol..dcol+96) (+)= A [128 x 96] * W^T with A in tensor memory (48 columns of fp16 pairs from acol)
     auto gemm_ts = [&](uint32_t wa, uint32_t acol, uint32_t dcol, uint32_t accumulate) {
       uint32_t b_lo = desc_lo(wa, W_LBO), acc = accumulate;
 #pragma unroll 2
