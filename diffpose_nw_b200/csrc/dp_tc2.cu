@@ -653,11 +653,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           const uint32_t b_lo = desc_lo(wa, OUT_LBO);
 #pragma unroll
           for (int part = 0; part < 3; ++part) {
-            const uint32_t a_lo = desc_lo(sbase + OFF_A + (part == 1 ? ABLK_BYTES : 0), A_LBO);
+            const uint32_t acol = part == 1 ? COL_TA1 : COL_TA0;     // X_hi, X_lo, X_hi as TMEM-resident A operands
 #pragma unroll
             for (int ks = 0; ks < 6; ++ks)
-              umma_ss(tb + COL_ACC, a_lo + ks * (2 * A_LBO >> 4), kHiK, b_lo + (part * 6 + ks) * (2 * OUT_LBO >> 4), kHiK, kN16,
-                      (part | ks) ? 1u : 0u, leader);
+              umma_ts(tb + COL_ACC, tb + acol + 8 * ks, b_lo + (part * 6 + ks) * (2 * OUT_LBO >> 4), kHiK, kN16, (part | ks) ? 1u : 0u, leader);
           }
         }
         w_release();
@@ -850,16 +849,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           launder<48>(u);
 #pragma unroll
           for (int i = 0; i < 48; ++i) v[i] += fmaxf(u[i], 0.f);   // closing residual of the last layer
-          uint8_t* d0 = smem + my_chunk;
+          // X = hi + lo, both fp16, both A operands in tensor memory (TA0, TA1)
+          uint32_t ph[24], pl[24];
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
             uint4 hi, lo;
             split8(v + 8 * q, hi, lo);
-            *reinterpret_cast<uint4*>(d0 + q * A_LBO) = hi;
-            *reinterpret_cast<uint4*>(d0 + ABLK_BYTES + q * A_LBO) = lo;
+            ph[4 * q] = hi.x; ph[4 * q + 1] = hi.y; ph[4 * q + 2] = hi.z; ph[4 * q + 3] = hi.w;
+            pl[4 * q] = lo.x; pl[4 * q + 1] = lo.y; pl[4 * q + 2] = lo.z; pl[4 * q + 3] = lo.w;
           }
+          tmem_st24_u32(ta0, ph);
+          tmem_st24_u32(ta1, pl);
         }
-        signal_ready(c);                                           // -> 11
+        signal_ready_tmem(c);                                      // -> 11
         wait_acc(c);
         if (hh == 0) {
           float u[16];
