@@ -89,7 +89,8 @@ constexpr int al16(int x) { return (x + 15) / 16 * 16; }
 constexpr int OFF_A = 0;                                   // three fp16 operand blocks; fp32 scratch [128][17] aliases block 0
 constexpr int OFF_SIDE = OFF_A + 3 * ABLK_BYTES;           // per operand block: the joint-16 rows of the 7 poses, compacted (rows 7..15 zero)
 constexpr int OFF_A16 = OFF_SIDE + 3 * SIDE_BYTES;         // per graph matrix (T1, T2, L^): element (18p+i, p) = G[i][16]
-constexpr int OFF_CS = OFF_A16 + 3 * A16_BYTES;            // Chebyshev slab: rows (1, 1, p1_hi, p1_hi, p1_lo, p2_hi, p2_hi, p2_lo), p_k = row sums of T_k
+constexpr int OFF_MK = OFF_A16 + 3 * A16_BYTES;            // key-mask chunk column: element (key row, 0) = -65504 for a masked joint, else 0
+constexpr int OFF_CS = OFF_MK + JS_BYTES;                  // Chebyshev slab: rows (1, 1, p1_hi, p1_hi, p1_lo, p2_hi, p2_hi, p2_lo), p_k = row sums of T_k
 constexpr int OFF_JS = OFF_CS + JS_BYTES;                  // joint slab of the current layer (fc1 bias + the LayerNorm shift seen through L^)
 constexpr int OFF_ONES = OFF_JS + JS_BYTES;                // constant-one K slab (bias rides in the MMA) + a zero chunk column
 constexpr int OFF_TALL = OFF_ONES + ONES_BYTES;            // tall T1, T2, L^
@@ -105,7 +106,7 @@ constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
 constexpr int SMEM_BYTES = OFF_TMEM + 16;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
-static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_CS % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_T12 % 16 == 0 && OFF_XT % 16 == 0 &&
+static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_CS % 16 == 0 && OFF_MK % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_T12 % 16 == 0 && OFF_XT % 16 == 0 &&
               OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && OFF_TEP % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
 
 __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -304,7 +305,11 @@ __device__ DP_PHASE_FN void ln_run(uint8_t* smem, uint32_t xcol, uint32_t acol, 
 // the warp loads the 64 columns from 18*p0 and every lane picks its pose's 17 with selects at compile-time offsets.
 // The probabilities go back to TMEM as fp16 pairs, zero outside the pose (block-diagonal P[128 x 128]), and feed the
 // P V product as its A operand.  One code path for all warps.
-__device__ DP_PHASE_FN void softmax_run(const uint8_t* smem, uint32_t region, int row, bool has_mask) {
+// The key mask (GraFormer.py:107-108, masked_fill(mask == 0, -1e9)) is not applied here: the second K step of the score
+// MMA multiplies a column of ones on the Q side with the mask chunk column on the K side, so a masked key arrives with
+// -65504 added to its score and its probability flushes to exactly 0 like the reference's.  k2 = log2(e)/sqrt(d_k), or 0
+// when every key is masked (the reference's softmax over seventeen equal -1e9 is uniform).
+__device__ DP_PHASE_FN void softmax_run(uint32_t region, int row, float k2) {
   const int p0 = ((row & ~31) * 57) >> 10;          // (32*wq) / 18 for wq = 0..3  ->  0, 1, 3, 5
   const int p = min(row / PS, TP - 1);              // pad rows 126, 127 ride along as pose 6
   const int q = p - p0;
@@ -313,17 +318,11 @@ __device__ DP_PHASE_FN void softmax_run(const uint8_t* smem, uint32_t region, in
   for (int i = 0; i < 64; i += 16) tmem_ld16_async(region + PS * p0 + i, v + i);
   tmem_ld_wait();
   launder<64>(v);
-  const float k2 = 0.20412414523193151f * 1.4426950408889634f;   // log2(e) / sqrt(24): softmax(s / sqrt(d_k)) in base 2
   float sc[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) {
     const float t = q == 0 ? v[j] : v[PS + j];
     sc[j] = q == 2 ? v[2 * PS + j] : t;
-  }
-  if (has_mask) {
-    const float* maskf = reinterpret_cast<const float*>(smem + OFF_MASK);
-#pragma unroll
-    for (int j = 0; j < NP; ++j) sc[j] = maskf[j] == 0.f ? -1e9f * 4.898979485566356f : sc[j];   // masked_fill(-1e9) acts after the 1/sqrt(d_k) scaling
   }
   float m0 = fmaxf(sc[0], sc[1]), m1 = fmaxf(sc[2], sc[3]), m2 = fmaxf(sc[4], sc[5]), m3 = fmaxf(sc[6], sc[7]);
   m0 = fmaxf(m0, fmaxf(sc[8], sc[9])); m1 = fmaxf(m1, fmaxf(sc[10], sc[11])); m2 = fmaxf(m2, fmaxf(sc[12], sc[13])); m3 = fmaxf(m3, fmaxf(sc[14], sc[15]));
@@ -434,7 +433,19 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     const float p1h = __half2float(__float2half_rn(p1)), p2h = __half2float(__float2half_rn(p2));
     *reinterpret_cast<uint4*>(smem + OFF_CS + tid * 16) = make_uint4(pack2(1.f, 1.f), pack2(p1h, p1h), pack2(p1 - p1h, p2h), pack2(p2h, p2 - p2h));
   }
-  if (tid < 32) maskf[tid] = (tid >= 24 && tid < 24 + a.c_out) ? __ldg(w.bout + tid - 24) : ((tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f);   // [0,17) key mask, [24,29) output bias
+  if (tid < 32) {
+    int n_masked = 0;
+    if (a.mask) for (int j = 0; j < NP; ++j) n_masked += a.mask[j] == 0;
+    // [20] the softmax scale, [24,29) output bias
+    maskf[tid] = (tid >= 24 && tid < 24 + a.c_out) ? __ldg(w.bout + tid - 24)
+                 : (tid == 20 ? (n_masked == NP ? 0.f : 0.20412414523193151f * 1.4426950408889634f) : 0.f);   // log2(e) / sqrt(24)
+  }
+  if (a.mask != nullptr && tid >= 32 && tid < 32 + TR) {
+    int n_masked = 0;
+    for (int j = 0; j < NP; ++j) n_masked += a.mask[j] == 0;
+    const int r = tid - 32, j = r % PS;
+    if (j < NP && a.mask[j] == 0 && n_masked < NP) *reinterpret_cast<__half*>(smem + OFF_MK + r * 16) = __float2half_rn(-65504.f);
+  }
   if (tid < NP * NP) t12[tid] = make_float2(__ldg(w.t1 + tid), __ldg(w.t2 + tid));
   fence_async_smem();
   tc_fence_before();
@@ -548,13 +559,14 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       umma_ss(tb + dcol, desc_lo(a16, (sbase + OFF_ONES + A_LBO) - a16), kHiK, desc_lo(sbase + OFF_SIDE + b_blk * SIDE_BYTES, 128), desc_hi(SIDE_LBO),
               kN96Mn, 1u, leader);
     };
-    // S_h[:, 0..128) = Q_h K_h^T; Q = block 0, K = block 1, chunk columns 3h..3h+2 (the 4th one of the second K step is
-    // the zero chunk column behind the ones slab for Q, whatever follows for K)
+    // S_h[:, 0..128) = Q_h K_h^T (+ key mask); Q = block 0, K = block 1, chunk columns 3h..3h+2.  The 4th chunk column of
+    // the second K step is reached through the descriptor's leading-dimension offset: the ones slab (1, 1, 0, ...) for Q
+    // and the key-mask chunk column (m_j, 0, 0, ...) for K, so that every score gets + m_j of its key
     auto scores_head = [&](int h, uint32_t dcol) {
       const uint32_t qa = sbase + OFF_A + 3 * h * A_LBO, ka = qa + ABLK_BYTES;
       umma_ss(tb + dcol, desc_lo(qa, A_LBO), kHiK, desc_lo(ka, A_LBO), kHiK, kN128, 0u, leader);
-      umma_ss(tb + dcol, desc_lo(qa + 2 * A_LBO, (sbase + OFF_ONES + A_LBO) - (qa + 2 * A_LBO)), kHiK, desc_lo(ka + 2 * A_LBO, A_LBO), kHiK, kN128,
-              1u, leader);
+      umma_ss(tb + dcol, desc_lo(qa + 2 * A_LBO, (sbase + OFF_ONES) - (qa + 2 * A_LBO)), kHiK,
+              desc_lo(ka + 2 * A_LBO, (sbase + OFF_MK) - (ka + 2 * A_LBO)), kHiK, kN128, 1u, leader);
     };
     // O[:, 24h..24h+32) = P_h V[:, 24h..24h+32): P_h in TMEM at pcol (slot layout, see softmax_run), V = block 2 in place as an
     // MN-major operand: one K=16 MMA per pose (joints 0..15), one for the joint-16 rows in the side buffer of block 2
@@ -677,7 +689,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     const int row = c.row, hh = c.hh;
     float* scratch = reinterpret_cast<float*>(smem + OFF_A);   // [128][SCR] fp32, aliases the head of operand block 0
     constexpr int SCR = 17;                                    // odd row stride: one thread per row reads without bank conflicts
-    const bool has_mask = a.mask != nullptr;
+    const float k2 = maskf[20];
     uint32_t ps = 0, pphase = 0;                               // parameter stage of the current layer
     const uint32_t xcol = c.tmem_lane + COL_X + hh * 48;       // this thread's half of its residual row
     const uint32_t my_chunk = (uint32_t)(OFF_A + a_chunk(row, hh * 6));   // its first chunk inside operand block 0
@@ -786,10 +798,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           wait_acc(c); epi_run(blk2, ocol, ninf, nullptr, 1.0f, false, side2, false, true);   // v
           signal_ready(c);                                           // v ready
           wait_acc(c);
-          softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
+          softmax_run(c.tmem_lane + (hh ? COL_S1 : COL_S0), row, k2);
           signal_ready_tmem(c);                                      // -> P V of heads 0, 1; scores of heads 2, 3
           wait_acc(c);
-          softmax_run(smem, c.tmem_lane + (hh ? COL_S1 : COL_S0), row, has_mask);
+          softmax_run(c.tmem_lane + (hh ? COL_S1 : COL_S0), row, k2);
           signal_ready_tmem(c);                                      // -> P V of heads 2, 3
           wait_acc(c);
           epi_tmem(ta0, ocol, 1.0f, false, false);

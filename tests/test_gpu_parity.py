@@ -180,6 +180,39 @@ def test_edge_cases_and_errors():
     assert (after - before - 1.0).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("engine", ["fp32", "auto"])
+@pytest.mark.parametrize("kind", ["all_true", "one_key", "sixteen", "all_masked"])
+def test_key_masks_vs_oracle(engine, kind):
+    """masked_fill(mask == 0, -1e9) before the softmax (GraFormer.py:107-108) for the masks the golden cases do not hold:
+    an explicit all-True mask (what the reference runner always passes), a single visible key, sixteen, and every key
+    masked -- where the reference's softmax over seventeen equal -1e9 is uniform.  The tensor-core engine applies the mask
+    inside the score MMA (a -65504 added through the spare K columns), so masked probabilities must be exactly zero."""
+    mask = torch.ones(1, 1, 17, dtype=torch.bool)
+    if kind == "one_key":
+        mask[:] = False
+        mask[0, 0, 9] = True
+    elif kind == "sixteen":
+        mask[0, 0, 16] = False
+    elif kind == "all_masked":
+        mask[:] = False
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(11)
+    model = D.FusedGCNdiff(adj, O.default_config())
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, seed=12, scale=0.02)
+    model.load_state_dict(sd)
+    model = model.to(dev()).set_engine(engine)
+    x = O.synthetic_poses(19, seed=23)
+    tt = torch.linspace(0, 40, 19)
+    ref = O.gcndiff_forward(sd, adj, 5, 4, x, mask, tt)
+    eps = model(x.to(dev()), mask.to(dev()), tt.to(dev()), 0).cpu()
+    tol = 2e-5 if engine == "fp32" else 3e-3 * ref.abs().max().item()
+    assert (eps - ref).abs().max().item() < tol
+    seq = [0, 12]
+    ref_s = O.ddim_sample(x, mask, seq, lambda a, m, t_: O.gcndiff_forward(sd, adj, 5, 4, a, m, t_), betas())[0][-1]
+    out = D.generalized_steps(x.to(dev()), mask.to(dev()), seq, model, betas())[0][-1].cpu()
+    assert (out - ref_s).abs().max().item() < (2e-5 if engine == "fp32" else 1e-3)
+
+
 def test_large_batch_properties():
     """BASELINE config 2 full size (B=1024): size-independent properties instead of an oracle run --
     batch-composition invariance (a pose's result does not depend on its neighbours or tile) and determinism."""
