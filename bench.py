@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_POSE_FORWARD = 24.65e6          # minimal algorithmic work, SURVEY.md section 8d
 ROW_BYTES = 17 * 5 * 4                   # one uvxyz pose, fp32
-NCU_DRAM_BYTES_PER_LAUNCH = 2033152      # configs[1], tc2_kernel: 2.03 MB read (weights + poses), 0 B written back (stays in L2)
+NCU_DRAM_BYTES_PER_LAUNCH = 2031744      # configs[1], tc2_kernel: 2.03 MB read (weights + poses), 0 B written back (stays in L2)
 METRIC = "poses/sec, full DDIM sampling (H hyps x T steps)"
 
 WORKLOADS = {
