@@ -233,3 +233,23 @@ def test_large_batch_properties():
     c32 = D.generalized_steps(x[perm].contiguous(), None, range(0, 24, 12), model, betas())[0][-1]
     assert torch.equal(c32, a32[perm])
     assert D._lib.launch_count() > 0
+
+
+def test_mask_device_copy_is_cached_and_follows_in_place_edits():
+    """The uint8 device copy of src_mask is kept across calls (the runner passes one persistent tensor); an in-place edit of
+    the caller's mask must still be seen."""
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(adj, O.default_config()).to(dev()).eval()
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    x = O.synthetic_poses(9, seed=3)
+    tt = torch.full((9,), 7.0)
+    mask = torch.ones(1, 1, 17, dtype=torch.bool, device=dev())
+    a = model(x.to(dev()), mask, tt.to(dev()), 0).cpu()
+    b = model(x.to(dev()), mask, tt.to(dev()), 0).cpu()
+    assert torch.equal(a, b) and model._mask_cache[2] is mask
+    mask[0, 0, 4] = False
+    c = model(x.to(dev()), mask, tt.to(dev()), 0).cpu()
+    ref = O.gcndiff_forward(sd, adj, 5, 4, x, mask.cpu(), tt)
+    assert (c - a).abs().max().item() > 1e-4
+    assert (c - ref).abs().max().item() < 3e-3 * ref.abs().max().item()
