@@ -77,6 +77,26 @@ def ddim_steps(b, seq, eta=0.0):
     return steps
 
 
+_STEP_CACHE = {}      # (betas identity, seq, eta) -> (DpStep array, betas kept alive); a handful of schedules per process
+
+
+def cached_ddim_steps(b, seq, eta):
+    """`ddim_steps` once per (beta schedule, sequence, eta).  The reference runner keeps `self.betas` on the GPU
+    (runners/diffpose_frame.py:49-50) and calls the sampler per batch: deriving the scalars each time would cost a
+    device->host copy (a stream synchronisation) plus T small CPU tensor programs per call -- more than the kernel
+    itself for the 2-step evaluation schedules."""
+    if not torch.is_tensor(b):
+        return ddim_steps(b, seq, eta)
+    key = (b.data_ptr(), b._version, b.numel(), str(b.device), b.dtype, tuple(int(s) for s in seq), float(eta))
+    hit = _STEP_CACHE.get(key)
+    if hit is None:
+        if len(_STEP_CACHE) >= 16:
+            _STEP_CACHE.clear()
+        hit = (ddim_steps(b, seq, eta), b)
+        _STEP_CACHE[key] = hit
+    return hit[0]
+
+
 def _unwrap(model):
     inner = getattr(model, "module", model)   # torch.nn.DataParallel wrapper (runners/diffpose_frame.py:127)
     if not isinstance(inner, FusedGCNdiff):
@@ -105,7 +125,7 @@ def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_inpu
             raise RuntimeError(f"x has {rows} rows, not a multiple of n_hyp={n_hyp}")
         n_pose = rows // n_hyp
     if steps is None:
-        steps = ddim_steps(b, seq, eta)
+        steps = cached_ddim_steps(b, seq, eta)
     T = len(steps)
     total = n_pose * n_hyp
     nz = None

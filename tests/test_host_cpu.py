@@ -154,3 +154,19 @@ def test_reference_checkpoint_list_and_ema(tmp_path):
         assert torch.equal(dict(dst.named_parameters())[k], v * 0.5)
     with pytest.raises(RuntimeError, match="no EMA shadow"):
         dst.load_checkpoint([sd, {}, 1, 2], use_ema=True)
+
+
+def test_step_scalars_are_cached_per_schedule():
+    """generalized_steps is called per batch with the same betas / seq / eta: the step scalars are derived once
+    (no device->host copy of betas per call), and an in-place change of the schedule is noticed."""
+    from diffpose_nw_b200 import sampler as S
+    b = torch.from_numpy(S.get_beta_schedule("linear", beta_start=1e-4, beta_end=1e-3, num_diffusion_timesteps=51)).float()
+    s1 = S.cached_ddim_steps(b, range(0, 24, 12), 0.0)
+    s2 = S.cached_ddim_steps(b, [0, 12], 0)
+    assert s1 is s2 and len(s1) == 2
+    ref = S.ddim_steps(b, [0, 12], 0.0)
+    assert all(abs(getattr(s1[k], f) - getattr(ref[k], f)) == 0 for k in range(2) for f in ("t", "sqrt_at", "sqrt_an", "c1", "c2"))
+    assert S.cached_ddim_steps(b, [0, 12], 1.0) is not s1
+    b.mul_(1.5)
+    s3 = S.cached_ddim_steps(b, [0, 12], 0.0)
+    assert s3 is not s1 and s3[0].sqrt_at != s1[0].sqrt_at
