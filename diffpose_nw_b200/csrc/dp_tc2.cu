@@ -513,7 +513,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     // D[:, dcol..dcol+96) (+)= A [128 x 96] * W^T with A in tensor memory (48 columns of fp16 pairs from acol)
     auto gemm_ts = [&](uint32_t wa, uint32_t acol, uint32_t dcol, uint32_t accumulate) {
       uint32_t b_lo = desc_lo(wa, W_LBO), acc = accumulate;
-#pragma unroll 2
+#pragma unroll
       for (int ks = 0; ks < 6; ++ks) {
         umma_ts(tb + dcol, tb + acol + 8 * ks, b_lo, kHiK, kN96, acc, leader);
         b_lo += 2 * W_LBO >> 4; acc = 1u;
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     // pairs of its own 48 channels (the two threads of a row convert their halves independently)
     auto gemm_ts_inplace = [&](uint32_t wa, uint32_t abase, uint32_t dcol, uint32_t accumulate) {
       uint32_t b_lo = desc_lo(wa, W_LBO), acc = accumulate;
-#pragma unroll 2
+#pragma unroll
       for (int ks = 0; ks < 6; ++ks) {
         umma_ts(tb + dcol, tb + abase + 8 * ks + (ks >= 3 ? 24 : 0), b_lo, kHiK, kN96, acc, leader);
         b_lo += 2 * W_LBO >> 4; acc = 1u;
