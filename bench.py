@@ -1,14 +1,15 @@
 #!/usr/bin/env python
 """bench.py -- poses/sec of full DDIM sampling (H hypotheses x T steps) through diffpose_nw_b200.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cpn1024|sweep]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cpn1024|gt1024x5|sweep|sweep1m|twostage|evalloop]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
            bench.py --gpus N --steps K --warmup W
 
 One "step" = one call of the hot path (`generalized_steps` -> dp_sample: all T DDIM steps of one batch in one
-persistent kernel) on one batch of synthetic Human3.6M-shaped poses.  Workload at every N (weak scaling: each rank
-processes its own batch): BASELINE.json configs[1] -- human36m_diffpose_uvxyz_cpn.yml shape, batch 1024, 1 hypothesis,
-seq = range(0,24,12) (T = 2), random-init weights.  Prints ONE JSON line on rank 0.
+persistent kernel) on one batch of synthetic Human3.6M-shaped poses.  Default workload at every N (weak scaling: each
+rank processes its own batch): BASELINE.json configs[1] -- human36m_diffpose_uvxyz_cpn.yml shape, batch 1024, 1 hypothesis,
+seq = range(0,24,12) (T = 2), random-init weights.  The other BASELINE configs are --workload choices (gt1024x5 = configs[2],
+strong-sharded over the ranks; sweep1m = configs[3] at any N; twostage = configs[4]).  Prints ONE JSON line on rank 0.
 
   value      device-timed throughput, inputs already resident in HBM (rotating through a pool larger than L2)
   e2e        same metric through the public API with pinned HOST buffers: H2D of x and D2H of x_T inside the timed region
@@ -32,35 +33,83 @@ sys.path.insert(0, ROOT)
 
 FLOP_PER_POSE_FORWARD = 24.65e6          # minimal algorithmic work, SURVEY.md section 8d
 ROW_BYTES = 17 * 5 * 4                   # one uvxyz pose, fp32
-NCU_DRAM_BYTES_PER_LAUNCH = 2031744      # configs[1], tc2_kernel: 2.03 MB read (weights + poses), 0 B written back (stays in L2)
 METRIC = "poses/sec, full DDIM sampling (H hyps x T steps)"
 
 WORKLOADS = {
     # BASELINE.json configs[1]: cpn.yml shape, batch 1024, H=1, config eval timesteps (2 of 24)
     "cpn1024": dict(batch=1024, n_hyp=1, seq=list(range(0, 24, 12)), eta=0.0,
                     name="configs[1]: human36m_diffpose_uvxyz_cpn.yml shape, batch 1024, H=1, seq=[0,12] (T=2), random-init"),
+    # the same batches through the evaluation loop of runners/diffpose_frame.py:365-387: sampler, then MPJPE / P-MPJPE partial sums
+    "evalloop": dict(batch=1024, n_hyp=1, seq=list(range(0, 24, 12)), eta=0.0, with_metrics=True,
+                     name="configs[1] + metrics per batch: sampler (batch 1024, H=1, T=2) followed by dp_metrics (MPJPE, P-MPJPE) as diffpose_frame.py:365-387"),
+    # BASELINE.json configs[2]: gt.yml shape (seq [0,6]), test_times=5, ONE batch of 1024 poses sharded over the ranks (strong scaling)
+    "gt1024x5": dict(batch=1024, n_hyp=5, seq=[0, 6], eta=1.0, scaling="strong",
+                     name="configs[2]: human36m_diffpose_uvxyz_gt.yml shape, batch 1024 sharded over the ranks, H=5 (fused mean), seq=[0,6] (T=2), eta=1 with device noise, random-init"),
     # a slice of BASELINE.json configs[3] (1M x 10 x 50 sweep): same H and T, 16384 poses per step
     "sweep": dict(batch=16384, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
                   name="slice of configs[3]: 16384 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
     # one tenth of BASELINE.json configs[3] in a single call: 100 000 poses x H=10 x T=50 (17 GB of device-drawn noise)
     "sweep100k": dict(batch=100000, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
                       name="tenth of configs[3]: 100000 poses x H=10 x T=50 (seq=range(50)), eta=1 with device noise, random-init"),
-    # BASELINE.json configs[3] itself when run on 8 GPUs: 1M poses x H=10 x T=50 in total, 125 000 poses per rank and call
-    "sweep1m_over8": dict(batch=125000, n_hyp=10, seq=list(range(0, 50)), eta=1.0,
-                          name="configs[3] at 8 ranks: 125000 poses per rank x H=10 x T=50 (1M poses in total on 8 GPUs), eta=1 with device noise, random-init"),
+    # BASELINE.json configs[3] itself at ANY number of ranks: 1M poses x H=10 x T=50 in total, sharded (strong scaling); the noise
+    # of a call is drawn in bounded chunks (sampler.sample: <= 2 GiB at a time)
+    "sweep1m": dict(batch=1000000, n_hyp=10, seq=list(range(0, 50)), eta=1.0, scaling="strong", draw_noise=True,
+                    name="configs[3]: 1M poses sharded over the ranks x H=10 x T=50 (seq=range(50)), eta=1 with device noise drawn per call, NCCL MPJPE reduction, random-init"),
     # BASELINE.json configs[4] per GPU: GCNpose lifts uv -> xyz, root-centre, concat, H=5 hypotheses refined by GCNdiff (gt.yml seq)
     "twostage": dict(batch=4096, n_hyp=5, seq=[0, 6], eta=0.0, two_stage=True,
                      name="configs[4]: GCNpose (uv->xyz) + GCNdiff refinement, batch 4096, H=5, seq=[0,6] (T=2), random-init"),
 }
 
 
-def load_peaks():
+def load_peaks(timed_region_s):
+    """bf16 peak the roofline is reported against: the burst figure for a kernel timed alone (< 1 s region), the sustained
+    one for a kernel timed inside a long step (the board reaches its power cap)."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    long_run = timed_region_s >= 1.0
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return dict(tflops=float(d.get("bf16_tflops", 1590.0)), hbm=float(d.get("hbm_gbs", 6650.0)), src="measured (MEASURED_PEAKS.json, bf16 burst)")
+        burst = float(d.get("bf16_tflops", 1590.0))
+        sus = float(d.get("bf16_tflops_sustained", burst))
+        return dict(tflops=sus if long_run else burst, hbm=float(d.get("hbm_gbs", 6650.0)),
+                    src="measured (MEASURED_PEAKS.json, bf16 %s)" % ("sustained: timed region >= 1 s" if long_run else "burst: timed region < 1 s"))
     return dict(tflops=1590.0, hbm=6650.0, src="fallback (B200_PROFILING.md)")
+
+
+def ncu_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum per tc2_kernel launch of configs[1], read from the newest committed
+    `ncu --set full` summary under profiles/ (tools/ncu_summary.py writes them); (None, why) when there is none."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_ncu_tcg_metrics.csv")))
+    if not files:
+        return None, "no profiles/*_ncu_tcg_metrics.csv"
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot, n = 0.0, 0
+    with open(files[-1]) as f:
+        for line in f:
+            c = line.strip().split(",")
+            if c[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and c[1] in mult:
+                vals = [float(v) for v in c[2:] if v]
+                tot += mult[c[1]] * sum(vals) / max(1, len(vals))
+                n += 1
+    if n != 2:
+        return None, f"{os.path.basename(files[-1])}: dram counters missing"
+    return int(round(tot)), f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per tc2_kernel launch (profiles/{os.path.basename(files[-1])})"
+
+
+def l2_note(pool_n, batch_bytes):
+    return (f"inputs rotate through a pool of {pool_n} distinct buffers = {pool_n * batch_bytes / 2**20:.0f} MiB (> 126 MiB L2), written once at set-up in "
+            "order, so every timed step reads a batch that is not cache resident; weights (1.6 MB) stay L2-resident by design")
+
+
+def bench_config(wl, world):
+    """The `config` object -- IDENTICAL in both arms (ours / reference) for the same command line."""
+    B = wl["batch"]
+    strong = wl.get("scaling") == "strong"
+    batch_bytes = (B // world if strong else B) * ROW_BYTES
+    pool_n = max(2, (int(126 * 2**20 * 1.1) + batch_bytes - 1) // batch_bytes)
+    return {"workload": wl["name"], "batch": B, "batch_is": "total, sharded over the ranks" if strong else "per GPU", "n_hyp": wl["n_hyp"],
+            "T": len(wl["seq"]), "eta": wl["eta"], "l2": l2_note(pool_n, batch_bytes)}, pool_n
 
 
 class ClockSampler:
@@ -165,9 +214,9 @@ def run_reference(args, wl):
     val = n * steps / dt
     sample = f"{n}-pose slice of the {wl['batch']}-pose batch per step, H={wl['n_hyp']}, T={len(wl['seq'])}, {steps} steps after {warm} warm-up"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "poses/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": wl["name"], "batch": wl["batch"], "n_hyp": wl["n_hyp"], "T": len(wl["seq"]),
-                                            "device": "host CPU", "torch_threads": torch.get_num_threads()},
+            "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": wl.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": bench_config(wl, int(os.environ.get("WORLD_SIZE", "1")))[0],
+            "detail": {"device": "host CPU", "torch_threads": torch.get_num_threads()},
             "cpu_baseline": {"value": val, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -181,7 +230,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cpn1024", choices=sorted(WORKLOADS))
-    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tc", "tcg"])
+    ap.add_argument("--engine", default="auto", choices=["auto", "fp32", "tcx", "tcg"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     wl = WORKLOADS[args.workload]
@@ -209,8 +258,14 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     torch.set_grad_enabled(False)
 
-    B, H, seq, eta = wl["batch"], wl["n_hyp"], wl["seq"], wl["eta"]
+    B_total, H, seq, eta = wl["batch"], wl["n_hyp"], wl["seq"], wl["eta"]
     T = len(seq)
+    strong = wl.get("scaling") == "strong"
+    if strong:                       # one workload-sized batch per step, sharded: this rank's contiguous pose range
+        lo, hi = D.shard_range(B_total, rank, world)
+        B = hi - lo
+    else:
+        B = B_total
     cfg = O.default_config()
     torch.manual_seed(0)
     model = D.FusedGCNdiff(D.adj_mx_from_edges(), cfg).to(dev).set_engine(args.engine)
@@ -218,16 +273,22 @@ def main():
     betas = torch.from_numpy(D.get_beta_schedule("linear", beta_start=1e-4, beta_end=1e-3, num_diffusion_timesteps=51)).float()
     steps_arr = D.ddim_steps(betas, seq, eta)
 
-    # input pool larger than L2 so every timed step reads inputs that are not cache resident
-    l2_bytes = 126 * 1024 * 1024
+    # input pool larger than L2, written once in order: every timed step reads a batch that is not cache resident
+    config, pool_n = bench_config(wl, world)
     batch_bytes = B * ROW_BYTES
-    pool_n = max(2, min(args.steps + args.warmup, (int(l2_bytes * 1.1) + batch_bytes - 1) // batch_bytes))
-    base = O.synthetic_poses(B, seed=1 + rank)
+    if B * pool_n > 4_000_000:       # bound the host-side generation for the million-pose workloads
+        pool_n = 2
+    base = O.synthetic_poses(min(B, 131072), seed=1 + rank)
+    if base.shape[0] < B:
+        base = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1)[:B].contiguous()
     g = torch.Generator().manual_seed(100 + rank)
-    pool = (base[None] + 0.01 * torch.randn(pool_n, 1, 17, 5, generator=g)).to(dev).contiguous()
+    pool = torch.empty(pool_n, B, 17, 5, device=dev)
+    base_dev = base.to(dev)
+    for i in range(pool_n):
+        pool[i] = base_dev + 0.01 * torch.randn(1, 17, 5, generator=g).to(dev)
     pool[:, :, 0, 2:] = 0
     noise = None
-    if eta > 0:
+    if eta > 0 and not wl.get("draw_noise"):
         noise = torch.randn(T, B * H, 17, 5, device=dev)
     targets = O.synthetic_targets(base).to(dev)
 
@@ -236,13 +297,18 @@ def main():
         torch.manual_seed(1)
         pose_model = D.FusedGCNpose(D.adj_mx_from_edges(), O.default_config(coords_dim=[2, 3])).to(dev).set_engine(args.engine).eval()
         uv_pool = pool[:, :, :, :2].contiguous()
+    msums = torch.zeros(3, device=dev, dtype=torch.float64)
 
     def step(i):
         if pose_model is not None:
-            return D.lift_and_refine(model, model_pose=pose_model, input_2d=uv_pool[i % pool_n], src_mask=None, seq=seq, betas=betas,
-                                     eta=eta, test_times=H)
-        return D.sample(model, pool[i % pool_n], None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True,
-                        mean_over_hyp=(H > 1), steps=steps_arr)
+            out = D.lift_and_refine(model, model_pose=pose_model, input_2d=uv_pool[i % pool_n], src_mask=None, seq=seq, betas=betas,
+                                    eta=eta, test_times=H)
+        else:
+            out = D.sample(model, pool[i % pool_n], None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True,
+                           mean_over_hyp=(H > 1), steps=steps_arr)
+        if wl.get("with_metrics"):
+            D.pose_error_sums(out, targets, sums=msums)
+        return out
 
     def barrier():
         if dist is not None:
@@ -270,56 +336,67 @@ def main():
         tms = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)
         ms = float(tms.item())
-    value = world * B * args.steps / (ms * 1e-3)
+    poses_per_step = B_total if strong else world * B        # whole job
+    value = poses_per_step * args.steps / (ms * 1e-3)
 
     # ---- end-to-end: pinned host buffers, H2D + D2H inside the timed region, public API (HostStream: the copies of
     #      neighbouring batches overlap the kernel of the current one; every step still moves its own input and output)
-    host_in = [torch.empty(B, 17, 5).pin_memory() for _ in range(2)]
-    host_in[0].copy_(base); host_in[1].copy_(base)
-    out_rows = B if H > 1 else B * H
     two_stage = pose_model is not None
-    hs = D.HostStream(model, batch=B, seq=seq, betas=betas, eta=eta, test_times=H) if (noise is None and not two_stage) else None
-    xd = torch.empty(B, 17, 5, device=dev)
-    if two_stage:       # the two-stage pipeline takes 2D keypoints from the host: [B,17,2] in, refined [B,17,5] out
-        host_uv = [base[:, :, :2].contiguous().pin_memory() for _ in range(2)]
-        uvd = torch.empty(B, 17, 2, device=dev)
-    host_out = [torch.empty(out_rows, 17, 5).pin_memory() for _ in range(2)]
+    out_rows = B if H > 1 else B * H
+    e2e = None
+    if B <= 131072:
+        host_in = [torch.empty(B, 17, 5).pin_memory() for _ in range(2)]
+        host_in[0].copy_(base); host_in[1].copy_(base)
+        hs = D.HostStream(model, batch=B, seq=seq, betas=betas, eta=eta, test_times=H) if (eta == 0 and not two_stage) else None
+        xd = torch.empty(B, 17, 5, device=dev)
+        if two_stage:       # the two-stage pipeline takes 2D keypoints from the host: [B,17,2] in, refined [B,17,5] out
+            host_uv = [base[:, :, :2].contiguous().pin_memory() for _ in range(2)]
+            uvd = torch.empty(B, 17, 2, device=dev)
+        host_out = [torch.empty(out_rows, 17, 5).pin_memory() for _ in range(2)]
 
-    def e2e_serial(i):      # eta > 0 with device noise: plain copy -> sample -> copy (HostStream draws no noise itself)
-        if two_stage:
-            uvd.copy_(host_uv[i & 1], non_blocking=True)
-            o = D.lift_and_refine(model, model_pose=pose_model, input_2d=uvd, src_mask=None, seq=seq, betas=betas, eta=eta, test_times=H)
+        def e2e_serial(i):      # eta > 0 with device noise: plain copy -> sample -> copy (HostStream draws no noise itself)
+            if two_stage:
+                uvd.copy_(host_uv[i & 1], non_blocking=True)
+                o = D.lift_and_refine(model, model_pose=pose_model, input_2d=uvd, src_mask=None, seq=seq, betas=betas, eta=eta, test_times=H)
+                host_out[i & 1].copy_(o, non_blocking=True)
+                return
+            xd.copy_(host_in[i & 1], non_blocking=True)
+            o = D.sample(model, xd, None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=(H > 1), steps=steps_arr)
+            if wl.get("with_metrics"):
+                D.pose_error_sums(o, targets, sums=msums)
             host_out[i & 1].copy_(o, non_blocking=True)
-            return
-        xd.copy_(host_in[i & 1], non_blocking=True)
-        o = D.sample(model, xd, None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=(H > 1), steps=steps_arr)
-        host_out[i & 1].copy_(o, non_blocking=True)
 
-    e_steps = max(3, min(args.steps, 200))
-    last = None
-    for i in range(3):
-        e2e_serial(i) if hs is None else hs.submit(host_in[i & 1])
-    if hs is not None:
-        hs.drain()
-    barrier()
-    t0 = time.perf_counter()
-    for i in range(e_steps):
-        if hs is None:
-            e2e_serial(i)
-        else:
-            r = hs.submit(host_in[i & 1])
-            last = r if r is not None else last
-    if hs is not None:
-        tail = hs.drain()
-        last = tail[-1]
-    torch.cuda.synchronize()
-    e_ms = (time.perf_counter() - t0) * 1e3
-    if dist is not None:
-        tms = torch.tensor([e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        e_ms = float(tms.item())
-    e2e_value = world * B * e_steps / (e_ms * 1e-3)
-    assert torch.isfinite(last if last is not None else host_out[0]).all()
+        if wl.get("with_metrics"):
+            hs = None
+        e_steps = max(3, min(args.steps, 200))
+        last = None
+        for i in range(3):
+            e2e_serial(i) if hs is None else hs.submit(host_in[i & 1])
+        if hs is not None:
+            hs.drain()
+        barrier()
+        t0 = time.perf_counter()
+        for i in range(e_steps):
+            if hs is None:
+                e2e_serial(i)
+            else:
+                r = hs.submit(host_in[i & 1])
+                last = r if r is not None else last
+        if hs is not None:
+            tail = hs.drain()
+            last = tail[-1]
+        torch.cuda.synchronize()
+        e_ms = (time.perf_counter() - t0) * 1e3
+        if dist is not None:
+            tms = torch.tensor([e_ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            e_ms = float(tms.item())
+        assert torch.isfinite(last if last is not None else host_out[0]).all()
+        e2e = {"value": poses_per_step * e_steps / (e_ms * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": B * 17 * 2 * 4 if two_stage else B * ROW_BYTES,
+               "d2h_bytes_per_step": out_rows * ROW_BYTES, "steps": e_steps, "ms_per_step": e_ms / e_steps,
+               "how": "pinned host buffers; " + ("HostStream (H2D / kernel / D2H of neighbouring batches overlap)" if hs is not None else "copy -> call -> copy per step")}
+    elif dist is not None:
+        barrier()
 
     # ---- the evaluation tail: per-rank partial sums + one all-reduce (NCCL) -- not part of the timed sampler region
     sums, _ = D.pose_error_sums(out, targets)
@@ -327,29 +404,27 @@ def main():
     clocks = sampler.stop() if sampler else None
 
     if rank == 0:
-        peaks = load_peaks()
+        peaks = load_peaks(ms * 1e-3)
         per_launch_s = ms * 1e-3 / args.steps
-        flops = B * H * T * FLOP_PER_POSE_FORWARD + (B * 25.2e6 if wl.get("two_stage") else 0.0)   # + GCNpose: 25.2 MFLOP/pose
+        flops = B * H * T * FLOP_PER_POSE_FORWARD + (B * 25.2e6 if two_stage else 0.0)   # per GPU; + GCNpose: 25.2 MFLOP/pose
         achieved = flops / per_launch_s / 1e12
-        hbm_bytes = B * ROW_BYTES + out_rows * ROW_BYTES + (T * B * H * ROW_BYTES if noise is not None else 0)
+        hbm_bytes = B * ROW_BYTES + out_rows * ROW_BYTES + (T * B * H * ROW_BYTES if eta > 0 else 0)
         ll = model.last_launch()
+        traffic, traffic_src = ncu_traffic() if (args.workload == "cpn1024" and model.engine() == "tcg") else (None, "measured for the cpn1024 workload only")
         line = {
             "metric": METRIC, "value": value, "unit": "poses/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16 operands / f32 accumulate (tcgen05)" if model.engine() in ("tc", "tcg") else "f32",
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+            "dtype": "f16 operands / f32 accumulate (tcgen05)" if model.engine() == "tcg" else ("f16 hi+lo operands / f32 accumulate (tcgen05)" if model.engine() == "tcx" else "f32"),
             "data": "synthetic",
-            "config": {"workload": wl["name"], "batch_per_gpu": B, "n_hyp": H, "T": T, "eta": eta, "engine": model.engine(),
-                       "l2": f"inputs rotate through a {pool_n * batch_bytes / 2**20:.0f} MiB pool (> 126 MiB L2) when steps+warmup >= {pool_n}; "
-                             "weights stay L2-resident by design",
+            "config": config,
+            "detail": {"engine": model.engine(), "lifter_engine": pose_model.forward_engine() if two_stage else None, "batch_this_rank": B,
                        "launch": {"grid": ll[0], "block": ll[1], "smem": ll[2], "poses_per_tile": ll[3], "tiles": ll[5]}},
-            "e2e": {"value": e2e_value, "unit": "poses/s", "h2d_bytes_per_step": B * 17 * 2 * 4 if two_stage else B * ROW_BYTES,
-                    "d2h_bytes_per_step": out_rows * ROW_BYTES, "steps": e_steps, "ms_per_step": e_ms / e_steps},
+            "e2e": e2e,
             "gpu_launches": int(launches),
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if (args.workload == "cpn1024" and model.engine() == "tcg") else None,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per tc2_kernel launch (profiles/r01e_ncu_tcg_metrics.csv)",
+                         "traffic": traffic, "traffic_source": traffic_src,
                          "peak_source": peaks["src"],
-                         "note": "achieved = 24.65 MFLOP x poses x H x T per dp_sample / mean device time of dp_sample (temb prologue + persistent kernel)",
+                         "note": "per GPU: achieved = 24.65 MFLOP x poses x H x T (+ 25.2 MFLOP x poses for the lifter) per step / mean device time of a step",
                          "hbm_gbs": hbm_bytes / per_launch_s / 1e9},
             "clocks": clocks,
             "eval": {"mpjpe_mm": mp, "p_mpjpe_mm": pmp, "poses": cnt},

@@ -10,7 +10,8 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libdiffpose_b200.so")
 
-ENGINE_AUTO, ENGINE_FP32, ENGINE_TC, ENGINE_TCG = 0, 1, 2, 3
+ENGINE_AUTO, ENGINE_FP32, ENGINE_TCX, ENGINE_TCG = 0, 1, 2, 3
+ENGINE_NAMES = {ENGINE_FP32: "fp32", ENGINE_TCX: "tcx", ENGINE_TCG: "tcg"}
 
 
 class DpStep(ctypes.Structure):
@@ -30,6 +31,9 @@ SIGNATURES = {
     "dp_pack": (_I, [_P, _P, _L, _P, _P]),
     "dp_set_engine": (_I, [_P, _I]),
     "dp_get_engine": (_I, [_P]),
+    "dp_get_forward_engine": (_I, [_P]),
+    "dp_device": (_I, [_P]),
+    "dp_lift": (_I, [_P, _P, _P, _P, _L, _P]),
     "dp_forward": (_I, [_P, _P, _P, _P, _P, _L, _P]),
     "dp_sample": (_I, [_P, _P, _I, _P, _L, _I, ctypes.POINTER(DpStep), _I, _P, _P, _I, _P]),
     "dp_metrics": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P]),

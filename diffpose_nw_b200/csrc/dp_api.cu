@@ -124,12 +124,16 @@ static void integerise_rows(const std::vector<float>& g, int n, std::vector<floa
   m.assign((size_t)n * n, 0.f);
   scale.assign(n, 1.f);
   for (int i = 0; i < n; ++i) {
+    // accept q only when r/q reproduces every entry within a FIXED absolute tolerance on g itself, 1e-6 max(1, |g|): wide
+    // enough for the fp32 rounding of the host-side 2 L L - I (a 17-term fp32 dot product; 2^-22 measurably rejects rows of
+    // the H36M skeleton and brings the fp16-rounding bias back: 0.07 mm MPJPE), and 100x tighter than what a rejected row
+    // gets instead (its entries rounded to fp16, 2^-12 relative) -- so accepting can only move the engine towards fp32
     int best = 0;
     for (int q = 1; q <= 4096 && !best; ++q) {
       bool ok = true;
       for (int j = 0; j < n && ok; ++j) {
-        const double v = (double)g[i * n + j] * q, r = std::nearbyint(v);
-        ok = std::fabs(v - r) <= 2e-6 * q && std::fabs(r) <= 2048.0;
+        const double gv = (double)g[i * n + j], r = std::nearbyint(gv * q);
+        ok = std::fabs(gv - r / q) <= 1e-6 * std::fmax(1.0, std::fabs(gv)) && std::fabs(r) <= 2048.0;
       }
       if (ok) best = q;
     }
@@ -237,6 +241,27 @@ static int pack_fp32(dp_model* m, const float* p, const float* adj_host, cudaStr
 
 using namespace dp;
 
+// The handle's buffers live on the device that was current at dp_create: a call made with another device current would
+// launch there with pointers into this one.  Refuse instead of faulting.
+static int check_device(dp_handle h, const char* what) {
+  int cur = -1;
+  DP_CUDA(cudaGetDevice(&cur));
+  if (cur != h->device) {
+    set_error(std::string(what) + ": the handle was created on device " + std::to_string(h->device) + " but device " + std::to_string(cur) +
+              " is current (create one handle per device; the Python shim re-creates it after model.to())");
+    return DP_ERR_STATE;
+  }
+  return DP_OK;
+}
+
+// engine that runs a forward call: AUTO -> the split-precision engine (a forward output is not damped by a DDIM schedule,
+// so it gets the accurate path), explicit settings are honoured
+static int forward_engine(dp_handle h) {
+  if (h->engine == DP_ENGINE_FP32 || !tc2_supported(h->d)) return DP_ENGINE_FP32;
+  if (h->engine == DP_ENGINE_TCG) return DP_ENGINE_TCG;
+  return DP_ENGINE_TCX;
+}
+
 extern "C" {
 
 int dp_create(dp_handle* out, int n_pts, int c_in, int c_out, int hid, int n_layer, int n_head, int has_temb) {
@@ -285,8 +310,9 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
     return DP_ERR_INVALID;
   }
   cudaStream_t s = static_cast<cudaStream_t>(stream);
+  DP_TRY(check_device(h, "dp_pack"));
   DP_TRY(pack_fp32(h, params, adj_host, s));
-  if (tc_supported(h->d)) DP_TRY(tc_pack(h, s));
+  tcx_invalidate(h);                          // the split-precision blocks are rebuilt lazily, on that engine's next use
   if (tc2_supported(h->d)) DP_TRY(tc2_pack(h, s));
   h->temb_t.clear();
   h->packed = true;
@@ -295,9 +321,9 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
 
 int dp_set_engine(dp_handle h, int engine) {
   DP_REQUIRE(h, "dp_set_engine: NULL handle");
-  DP_REQUIRE(engine == DP_ENGINE_AUTO || engine == DP_ENGINE_FP32 || engine == DP_ENGINE_TC || engine == DP_ENGINE_TCG, "dp_set_engine: unknown engine");
-  if ((engine == DP_ENGINE_TC && !tc_supported(h->d)) || (engine == DP_ENGINE_TCG && !tc2_supported(h->d))) {
-    set_error("dp_set_engine: the tensor-core engines need hid_dim=96, n_head=4, n_pts=17 (the first one also uvxyz in and out)");
+  DP_REQUIRE(engine == DP_ENGINE_AUTO || engine == DP_ENGINE_FP32 || engine == DP_ENGINE_TCX || engine == DP_ENGINE_TCG, "dp_set_engine: unknown engine");
+  if ((engine == DP_ENGINE_TCX && !tcx_supported(h->d)) || (engine == DP_ENGINE_TCG && !tc2_supported(h->d))) {
+    set_error("dp_set_engine: the tensor-core engines need hid_dim=96, n_head=4, n_pts=17 and coords_dim <= 5");
     return DP_ERR_UNSUPPORTED;
   }
   h->engine = engine;
@@ -307,8 +333,13 @@ int dp_set_engine(dp_handle h, int engine) {
 int dp_get_engine(dp_handle h) {
   if (!h) return DP_ERR_INVALID;
   if (h->engine == DP_ENGINE_FP32 || !tc2_supported(h->d)) return DP_ENGINE_FP32;
-  if (h->engine == DP_ENGINE_TC) return tc_supported(h->d) ? DP_ENGINE_TC : DP_ENGINE_TCG;
-  return DP_ENGINE_TCG;   // AUTO = the second-generation tensor-core engine
+  if (h->engine == DP_ENGINE_TCX) return DP_ENGINE_TCX;
+  return DP_ENGINE_TCG;   // AUTO = the fp16-operand tensor-core engine (its error is damped by the DDIM schedule)
+}
+
+int dp_get_forward_engine(dp_handle h) {
+  if (!h) return DP_ERR_INVALID;
+  return forward_engine(h);
 }
 
 int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char* mask, float* out, long n, void* stream) {
@@ -317,12 +348,32 @@ int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char*
   if (!h->packed) { set_error("dp_forward: dp_pack has not been called"); return DP_ERR_STATE; }
   DP_REQUIRE(!h->d.has_temb || t != nullptr, "dp_forward: t is required for the diffusion denoiser");
   if (n == 0) return DP_OK;
+  DP_TRY(check_device(h, "dp_forward"));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   // Per-sample timesteps need a per-sample embedding table (computed in chunks into the same buffer the sampler caches
-  // its per-step table in, so that cache is dropped).  The first tensor-core engine has no forward entry: it falls to fp32.
-  h->temb_t.clear();
-  if (dp_get_engine(h) == DP_ENGINE_TCG) return tc2_forward(h, x, t, mask, out, n, s);
+  // its per-step table in, so that cache is dropped).
+  if (h->d.has_temb) h->temb_t.clear();
+  const int eng = forward_engine(h);
+  if (eng == DP_ENGINE_TCX) return tcx_forward(h, x, t, mask, out, n, 0, s);
+  if (eng == DP_ENGINE_TCG) return tc2_forward(h, x, t, mask, out, n, s);
   return simt_forward(h, x, t, mask, out, n, s);
+}
+
+int dp_lift(dp_handle h, const float* uv, const unsigned char* mask, float* out_uvxyz, long n, void* stream) {
+  DP_REQUIRE(h && uv && out_uvxyz, "dp_lift: NULL argument");
+  DP_REQUIRE(n >= 0, "dp_lift: negative batch");
+  DP_REQUIRE(!h->d.has_temb, "dp_lift: the handle must be a GCNpose lifter (has_temb = 0)");
+  if (!h->packed) { set_error("dp_lift: dp_pack has not been called"); return DP_ERR_STATE; }
+  if (n == 0) return DP_OK;
+  DP_TRY(check_device(h, "dp_lift"));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int eng = forward_engine(h);
+  if (eng == DP_ENGINE_TCX) return tcx_forward(h, uv, nullptr, mask, out_uvxyz, n, 1, s);   // glue fused into the kernel's store
+  const Dims& d = h->d;
+  DP_TRY(ensure_capacity(&h->lift_scratch, &h->lift_cap, (size_t)n * d.n_pts * d.c_out));
+  if (eng == DP_ENGINE_TCG) DP_TRY(tc2_forward(h, uv, nullptr, mask, h->lift_scratch, n, s));
+  else DP_TRY(simt_forward(h, uv, nullptr, mask, h->lift_scratch, n, s));
+  return lift_glue_launch(uv, h->lift_scratch, out_uvxyz, n, d.n_pts, d.c_in, d.c_out, s);
 }
 
 int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
@@ -333,6 +384,7 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
   DP_REQUIRE(h->d.has_temb, "dp_sample: handle was created with has_temb = 0 (GCNpose has no sampler)");
   if (!h->packed) { set_error("dp_sample: dp_pack has not been called"); return DP_ERR_STATE; }
   if (n_pose == 0) return DP_OK;
+  DP_TRY(check_device(h, "dp_sample"));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const Dims& d = h->d;
 
@@ -341,15 +393,21 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
   if (n_steps <= kMaxInlineSteps) {
     std::memcpy(inl.s, steps_host, n_steps * sizeof(dp_step));
   } else {
-    if (h->steps_cap < (size_t)n_steps) {
-      if (h->steps) cudaFree(h->steps);
-      h->steps = nullptr; h->steps_cap = 0;
-      DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->steps), (size_t)n_steps * sizeof(dp_step)));
-      h->steps_cap = n_steps;
+    // long schedules (> 64 steps) live in a device buffer that is uploaded when the schedule CHANGES, not per call; the
+    // upload reads the handle's own copy, and the one synchronisation below only happens on such a change
+    const bool same = h->steps != nullptr && h->steps_host.size() == (size_t)n_steps &&
+                      std::memcmp(h->steps_host.data(), steps_host, n_steps * sizeof(dp_step)) == 0;
+    if (!same) {
+      if (h->steps_cap < (size_t)n_steps) {
+        if (h->steps) cudaFree(h->steps);
+        h->steps = nullptr; h->steps_cap = 0;
+        DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&h->steps), (size_t)n_steps * sizeof(dp_step)));
+        h->steps_cap = n_steps;
+      }
+      h->steps_host.assign(steps_host, steps_host + n_steps);
+      DP_CUDA(cudaMemcpyAsync(h->steps, h->steps_host.data(), n_steps * sizeof(dp_step), cudaMemcpyHostToDevice, s));
+      DP_CUDA(cudaStreamSynchronize(s));
     }
-    // long schedules only: steps_host is caller (possibly pageable) memory, so finish the copy before returning
-    DP_CUDA(cudaMemcpyAsync(h->steps, steps_host, n_steps * sizeof(dp_step), cudaMemcpyHostToDevice, s));
-    DP_CUDA(cudaStreamSynchronize(s));
     steps_dev = h->steps;
   }
   // batch-invariant time embeddings: one row per step (models/gcndiff.py:103-106, :51).  The table depends only
@@ -365,6 +423,9 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
     }
   }
 
+  const int eng = dp_get_engine(h);
+  // default engine: the hypothesis mean is fused into the kernel's final store (one launch, no [H*B] scratch)
+  if (eng == DP_ENGINE_TCG) return tc2_sample(h, x_in, x_is_repeated, x_out, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, mean_over_hyp, s);
   float* dst = x_out;
   const int row_floats = d.n_pts * d.c_out;
   if (mean_over_hyp && n_hyp > 1) {
@@ -372,11 +433,8 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
     dst = h->hyp_scratch;
   }
   int rc;
-  const int eng = dp_get_engine(h);
-  if (eng == DP_ENGINE_TCG)
-    rc = tc2_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
-  else if (eng == DP_ENGINE_TC)
-    rc = tc_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
+  if (eng == DP_ENGINE_TCX)
+    rc = tcx_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
   else
     rc = simt_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
   if (rc != DP_OK) return rc;
@@ -428,17 +486,19 @@ int dp_last_launch_info(dp_handle h, long* out6) {
 }
 
 const char* dp_last_error(void) { return g_err.c_str(); }
-const char* dp_version(void) { return "diffpose_b200 0.1 (sm_100a)"; }
+const char* dp_version(void) { return "diffpose_b200 0.2 (sm_100a)"; }
+int dp_device(dp_handle h) { return h ? h->device : DP_ERR_INVALID; }
 
 void dp_destroy(dp_handle h) {
   if (!h) return;
-  tc_free(h);
+  tcx_free(h);
   tc2_free(h);
   if (h->blob) cudaFree(h->blob);
   if (h->dw) cudaFree(h->dw);
   if (h->temb) cudaFree(h->temb);
   if (h->steps) cudaFree(h->steps);
   if (h->hyp_scratch) cudaFree(h->hyp_scratch);
+  if (h->lift_scratch) cudaFree(h->lift_scratch);
   delete h;
 }
 

@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "../../include/diffpose_b200.h"
+#include "../../include/diffpose_b200_diag.h"
 
 namespace dp {
 
@@ -75,7 +76,7 @@ struct StepsArg {
   dp_step s[kMaxInlineSteps];
 };
 
-struct TcPack;   // defined in dp_tc.cu
+struct TcxPack;  // defined in dp_tcx.cu
 struct Tc2Pack;  // defined in dp_tc2.cu
 
 }  // namespace dp
@@ -99,11 +100,14 @@ struct dp_model {
   std::vector<float> temb_t;      // timesteps the table currently holds (sampler schedule cache; empty = invalid)
   dp_step* steps = nullptr;       // device copy of the step scalars, only used when n_steps > kMaxInlineSteps
   size_t steps_cap = 0;
-  float* hyp_scratch = nullptr;   // [n_pose*n_hyp, n_pts, c] when the hypothesis mean is fused after sampling
+  std::vector<dp_step> steps_host;   // what `steps` currently holds (a long schedule is uploaded once, not per call)
+  float* hyp_scratch = nullptr;   // [n_pose*n_hyp, n_pts, c]: hypothesis mean of the engines that do not fuse it (fp32, tcx)
   size_t hyp_cap = 0;
+  float* lift_scratch = nullptr;  // [n, n_pts, c_out]: dp_lift on the engines that do not fuse the glue
+  size_t lift_cap = 0;
 
-  dp::TcPack* tc = nullptr;       // tensor-core engine state (fp16 packed weights, ...)
-  dp::Tc2Pack* tc2 = nullptr;     // second-generation tensor-core engine state
+  dp::TcxPack* tcx = nullptr;     // split-precision tensor-core engine state (hi/lo fp16 weight blocks, packed lazily)
+  dp::Tc2Pack* tc2 = nullptr;     // default tensor-core engine state
   long last_launch[6] = {0, 0, 0, 0, 0, 0};
   long long* trace = nullptr;     // caller-owned device buffer for the hand-over timestamps (dp_set_trace)
   int trace_cap = 0;
@@ -119,13 +123,15 @@ int simt_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out,
                 const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
                 const unsigned char* mask, cudaStream_t s);
 int ensure_capacity(float** p, size_t* cap, size_t need_floats);
-// dp_tc.cu
-bool tc_supported(const Dims& d);
-int tc_pack(dp_model* m, cudaStream_t s);
-void tc_free(dp_model* m);
-int tc_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
-              const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
-              const unsigned char* mask, cudaStream_t s);
+// dp_tcx.cu
+bool tcx_supported(const Dims& d);
+void tcx_invalidate(dp_model* m);   // after dp_pack: the split weights are rebuilt on the engine's next use
+void tcx_free(dp_model* m);
+int tcx_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
+               const unsigned char* mask, cudaStream_t s);
+int tcx_forward(dp_model* m, const float* x, const float* t, const unsigned char* mask, float* out, long n, int emit_uvxyz, cudaStream_t s);
+// dp_lab.cu
 int tc_lab(const void* image_dev, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* out_dev, int ncols,
            const void* tmem_image_dev, int tmem_col0, int tmem_ncols, cudaStream_t s);
 void tc_lab_cycles(long long* out2);
@@ -136,11 +142,14 @@ int tc2_pack(dp_model* m, cudaStream_t s);
 // after simt_temb filled m->temb for a sampler schedule: the same embeddings as GC2 bias blocks of the tcg engine
 int tc2_tau(dp_model* m, int n_steps, cudaStream_t s);
 void tc2_free(dp_model* m);
+// mean_over_hyp: x_out is [n_pose, n_pts, c], the hypothesis mean fused into the kernel's final store
 int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
                const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
-               const unsigned char* mask, cudaStream_t s);
+               const unsigned char* mask, int mean_over_hyp, cudaStream_t s);
 // dp_metrics.cu
 int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                    double* sums, float* per_pose, cudaStream_t s);
 int hyp_mean_launch(const float* x, float* out, long n_pose, int n_hyp, int row_floats, cudaStream_t s);
+// out[n][n_pts][c_in + c_out] = [uv | xyz - xyz[root]] (runners/diffpose_frame.py:337-343 with out-of-place root-centring)
+int lift_glue_launch(const float* uv, const float* xyz, float* out, long n, int n_pts, int c_in, int c_out, cudaStream_t s);
 }  // namespace dp

@@ -99,49 +99,64 @@ __device__ inline double det3(const double m[3][3]) {
          m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
 }
 
-__global__ void metrics_kernel(const float* __restrict__ pred, int ps, int po, const float* __restrict__ gt, long n,
-                               double* __restrict__ sums, float* __restrict__ per_pose) {
-  const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
-  double e1 = 0.0, e2 = 0.0, cnt = 0.0;
-  if (i < n) {
-    double X[NP][3], Y[NP][3];  // X = target, Y = predicted, both root-centred (out of place)
-    const float* p = pred + (size_t)i * NP * ps + po;
-    const float* g = gt + (size_t)i * NP * 3;
-    const float pr[3] = {p[0], p[1], p[2]}, gr[3] = {g[0], g[1], g[2]};
-    float acc = 0.f;
-    for (int j = 0; j < NP; ++j) {
-      float d2 = 0.f;
+__device__ __forceinline__ double warp_sum_d(double v) {
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const float pv = p[j * ps + c] - pr[c], gv = g[j * 3 + c] - gr[c];
-        Y[j][c] = pv; X[j][c] = gv;
-        const float df = pv - gv;
-        d2 += df * df;
-      }
-      acc += sqrtf(d2);
-    }
-    e1 = (double)(acc / (float)NP);
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
 
-    double mx[3] = {0, 0, 0}, my[3] = {0, 0, 0};
-    for (int j = 0; j < NP; ++j)
+// One WARP per pose: lane j < 17 owns joint j of the prediction and the target; every per-pose sum is a warp shuffle
+// reduction (fp64, like the reference's numpy), and the 3x3 SVD -- a register-only Jacobi iteration -- runs redundantly
+// on all lanes (no divergence, no local-memory arrays).  A block of 8 warps handles 8 poses, so 1024 poses already
+// spread over 128 CTAs (the first version ran one thread per pose with 34x3 doubles of local memory on 8 CTAs: 44 us
+// per 1024 poses, half a sampler launch).
+constexpr int kMetricWarps = 8;
+__global__ void __launch_bounds__(kMetricWarps * 32) metrics_kernel(const float* __restrict__ pred, int ps, int po, const float* __restrict__ gt, long n,
+                                                                    double* __restrict__ sums, float* __restrict__ per_pose) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double e1s = 0.0, e2s = 0.0, cnt = 0.0;      // this warp's partial sums (identical on every lane)
+  for (long i = (long)blockIdx.x * kMetricWarps + warp; i < n; i += (long)gridDim.x * kMetricWarps) {
+    const int j = lane < NP ? lane : 0;
+    const float* p = pred + (size_t)i * NP * ps + po + j * ps;
+    const float* g = gt + (size_t)i * NP * 3 + j * 3;
+    float pv[3], gv[3];
 #pragma unroll
-      for (int c = 0; c < 3; ++c) { mx[c] += X[j][c]; my[c] += Y[j][c]; }
+    for (int c = 0; c < 3; ++c) { pv[c] = p[c]; gv[c] = g[c]; }
+    // out-of-place root-centring of both (runners/diffpose_frame.py:384-385, intended semantics)
+    float d2 = 0.f;
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { mx[c] /= NP; my[c] /= NP; }
-    double nx = 0, ny = 0;
-    for (int j = 0; j < NP; ++j)
+    for (int c = 0; c < 3; ++c) {
+      pv[c] -= __shfl_sync(0xffffffffu, pv[c], 0);
+      gv[c] -= __shfl_sync(0xffffffffu, gv[c], 0);
+      const float df = pv[c] - gv[c];
+      d2 += df * df;
+    }
+    const bool live = lane < NP;
+    // mpjpe (common/loss.py:7-13): mean over joints of the fp32 joint distance
+    float acc = live ? sqrtf(d2) : 0.f;
 #pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double a = X[j][c] - mx[c], b = Y[j][c] - my[c];
-        nx += a * a; ny += b * b;
-      }
-    nx = sqrt(nx); ny = sqrt(ny);
-    double h[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};  // H = X0^T Y0
-    for (int j = 0; j < NP; ++j)
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const double e1 = (double)(acc / (float)NP);
+
+    // p_mpjpe (common/loss.py:25-64): X = target, Y = prediction
+    double X[3], Y[3], mx[3], my[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)
+    for (int c = 0; c < 3; ++c) { X[c] = live ? (double)gv[c] : 0.0; Y[c] = live ? (double)pv[c] : 0.0; }
 #pragma unroll
-        for (int b = 0; b < 3; ++b) h[a][b] += ((X[j][a] - mx[a]) / nx) * ((Y[j][b] - my[b]) / ny);
+    for (int c = 0; c < 3; ++c) { mx[c] = warp_sum_d(X[c]) / NP; my[c] = warp_sum_d(Y[c]) / NP; }
+    double a0[3], b0[3], nx = 0.0, ny = 0.0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      a0[c] = live ? X[c] - mx[c] : 0.0;
+      b0[c] = live ? Y[c] - my[c] : 0.0;
+      nx += a0[c] * a0[c]; ny += b0[c] * b0[c];
+    }
+    nx = sqrt(warp_sum_d(nx)); ny = sqrt(warp_sum_d(ny));
+    double h[3][3];                                         // H = X0^T Y0 of the normalised, centred point sets
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) h[a][b] = warp_sum_d((a0[a] / nx) * (b0[b] / ny));
     double u[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, v[3][3], sv[3];
     svd3(h, u, sv, v);
     double r[3][3];
@@ -159,39 +174,40 @@ __global__ void metrics_kernel(const float* __restrict__ pred, int ps, int po, c
 #pragma unroll
       for (int b = 0; b < 3; ++b) r[a][b] = v[a][0] * u[b][0] + v[a][1] * u[b][1] + v[a][2] * u[b][2];
     const double scale = (sv[0] + sv[1] + sv[2]) * nx / ny;
-    double tr[3];
+    double e = 0.0;
 #pragma unroll
-    for (int b = 0; b < 3; ++b) tr[b] = mx[b] - scale * (my[0] * r[0][b] + my[1] * r[1][b] + my[2] * r[2][b]);
-    double err = 0.0;
-    for (int j = 0; j < NP; ++j) {
-      double d2 = 0.0;
-#pragma unroll
-      for (int b = 0; b < 3; ++b) {
-        const double al = scale * (Y[j][0] * r[0][b] + Y[j][1] * r[1][b] + Y[j][2] * r[2][b]) + tr[b];
-        const double df = al - X[j][b];
-        d2 += df * df;
-      }
-      err += sqrt(d2);
+    for (int b = 0; b < 3; ++b) {
+      const double tr = mx[b] - scale * (my[0] * r[0][b] + my[1] * r[1][b] + my[2] * r[2][b]);
+      const double al = scale * (Y[0] * r[0][b] + Y[1] * r[1][b] + Y[2] * r[2][b]) + tr;
+      const double df = al - X[b];
+      e += df * df;
     }
-    e2 = err / NP;
-    cnt = 1.0;
-    if (per_pose) { per_pose[2 * i] = (float)e1; per_pose[2 * i + 1] = (float)e2; }
+    const double e2 = warp_sum_d(live ? sqrt(e) : 0.0) / NP;
+    e1s += e1; e2s += e2; cnt += 1.0;
+    if (per_pose && lane == 0) { per_pose[2 * i] = (float)e1; per_pose[2 * i + 1] = (float)e2; }
   }
   // block reduction -> one atomic per block and quantity
-  __shared__ double red[3][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    e1 += __shfl_xor_sync(0xffffffffu, e1, o);
-    e2 += __shfl_xor_sync(0xffffffffu, e2, o);
-    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
-  }
-  if (lane == 0) { red[0][warp] = e1; red[1][warp] = e2; red[2][warp] = cnt; }
+  __shared__ double red[3][kMetricWarps];
+  if (lane == 0) { red[0][warp] = e1s; red[1][warp] = e2s; red[2][warp] = cnt; }
   __syncthreads();
   if (threadIdx.x < 3) {
     double s = 0.0;
-    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[threadIdx.x][w];
-    atomicAdd(sums + threadIdx.x, s);
+    for (int w = 0; w < kMetricWarps; ++w) s += red[threadIdx.x][w];
+    if (s != 0.0) atomicAdd(sums + threadIdx.x, s);
+  }
+}
+
+// [uv | xyz - xyz[root]]: the glue between the lifter and the sampler for the engines whose forward kernel does not
+// write it directly (runners/diffpose_frame.py:337-343 with the intended out-of-place root-centring)
+__global__ void lift_glue_kernel(const float* __restrict__ uv, const float* __restrict__ xyz, float* __restrict__ out, long n, int n_pts,
+                                 int c_in, int c_out) {
+  const int wd = c_in + c_out;
+  const long total = n * n_pts * wd;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long row = i / wd;
+    const int c = (int)(i - row * wd);
+    const long pose = row / n_pts;
+    out[i] = c < c_in ? uv[row * c_in + c] : __fsub_rn(xyz[row * c_out + (c - c_in)], xyz[pose * n_pts * c_out + (c - c_in)]);
   }
 }
 
@@ -200,9 +216,9 @@ __global__ void metrics_kernel(const float* __restrict__ pred, int ps, int po, c
 int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                    double* sums, float* per_pose, cudaStream_t s) {
   (void)n_pts;
-  const int block = 128;
-  const long grid = (n + block - 1) / block;
-  metrics_kernel<<<(unsigned)grid, block, 0, s>>>(pred, pred_stride, pred_offset, gt, n, sums, per_pose);
+  long grid = (n + kMetricWarps - 1) / kMetricWarps;
+  if (grid > 148 * 8) grid = 148 * 8;
+  metrics_kernel<<<(unsigned)grid, kMetricWarps * 32, 0, s>>>(pred, pred_stride, pred_offset, gt, n, sums, per_pose);
   count_launch();
   DP_CUDA(cudaGetLastError());
   return DP_OK;
@@ -213,6 +229,16 @@ int hyp_mean_launch(const float* x, float* out, long n_pose, int n_hyp, int row_
   long grid = (total + 255) / 256;
   if (grid > 148 * 8) grid = 148 * 8;
   hyp_mean_kernel<<<(unsigned)grid, 256, 0, s>>>(x, out, n_pose, n_hyp, row_floats);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
+
+int lift_glue_launch(const float* uv, const float* xyz, float* out, long n, int n_pts, int c_in, int c_out, cudaStream_t s) {
+  const long total = n * n_pts * (c_in + c_out);
+  long grid = (total + 255) / 256;
+  if (grid > 148 * 8) grid = 148 * 8;
+  lift_glue_kernel<<<(unsigned)grid, 256, 0, s>>>(uv, xyz, out, n, n_pts, c_in, c_out);
   count_launch();
   DP_CUDA(cudaGetLastError());
   return DP_OK;

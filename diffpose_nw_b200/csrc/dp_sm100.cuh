@@ -184,14 +184,18 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
   launder<16>(v);
 }
 
+// fp32 pair -> packed fp16 pair, SATURATING (F2FP.SATFINITE, same cost as the plain conversion): |v| > 65504 becomes
+// +-65504 instead of inf, so an out-of-range activation of a trained checkpoint can never turn into inf - inf = NaN inside
+// an MMA; NaN inputs stay NaN.  The fp16 operand range is a documented limit of the tensor-core engines.
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
-  __half2 h = __floats2half2_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+  uint32_t d;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));   // first source -> upper half
+  return d;
 }
 // relu fused into the conversion (F2FP.RELU): negative -> +0, NaN stays NaN like torch.relu
 __device__ __forceinline__ uint32_t pack2_relu(float a, float b) {
   uint32_t d;
-  asm("cvt.rn.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));   // first source -> upper half
+  asm("cvt.rn.satfinite.relu.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));   // first source -> upper half
   return d;
 }
 __device__ __forceinline__ uint4 pack8_relu(const float* v) {
@@ -221,11 +225,10 @@ __device__ __forceinline__ void split8(const float* v, uint4& hi, uint4& lo) {
   uint32_t h[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const __half2 hh = __floats2half2_rn(v[2 * i], v[2 * i + 1]);
-    const float2 f = __half22float2(hh);
+    h[i] = pack2(v[2 * i], v[2 * i + 1]);
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[i]));
     r[2 * i] = v[2 * i] - f.x;
     r[2 * i + 1] = v[2 * i + 1] - f.y;
-    h[i] = *reinterpret_cast<const uint32_t*>(&hh);
   }
   hi = make_uint4(h[0], h[1], h[2], h[3]);
   lo = pack8(r);

@@ -129,6 +129,10 @@ struct Tc2Args {
   int x_is_repeated;
   float* out;
   long n_rows, n_pose;
+  int n_hyp;
+  int mean_over_hyp;         // sampler: out = mean over the hypotheses of a pose, [n_pose][17][c] (runners/diffpose_frame.py:382).
+                             // Rows are then walked pose-major (row g = pose g / n_hyp, hypothesis g % n_hyp) and every CTA owns a
+                             // contiguous range of POSES, so all hypotheses of a pose pass through the same CTA in order
   int n_steps;
   const float* temb;         // [n_rows][n_layer][96]: per-sample time embeddings of a forward call (forward_only)
   const uint8_t* tau;        // [n_steps][n_layer][LP_TAU_BYTES]: the sampler's time embedding as a bias block of GC2 (tc2_tau)
@@ -456,7 +460,20 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
   // let the next kernel of the stream begin its launch: its CTAs take over each SM as ours retire
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-  const int n_tiles = (int)((a.n_rows + TP - 1) / TP);   // the host refuses more than INT_MAX tiles
+  // Tile schedule of this CTA.  Default: tiles blockIdx.x, blockIdx.x + gridDim.x, ... of the hypothesis-major row list.
+  // mean_over_hyp: a contiguous, balanced range of poses; its n_hyp rows per pose form this CTA's own tile list.
+  long row_lo = 0, row_hi = 0;
+  int my_tiles;
+  if (a.mean_over_hyp) {
+    const long base = a.n_pose / gridDim.x, rem = a.n_pose % gridDim.x;
+    const long p_lo = blockIdx.x * base + min((long)blockIdx.x, rem);
+    row_lo = p_lo * a.n_hyp;
+    row_hi = row_lo + (base + ((long)blockIdx.x < rem ? 1 : 0)) * a.n_hyp;
+    my_tiles = (int)((row_hi - row_lo + TP - 1) / TP);
+  } else {
+    const int n_tiles = (int)((a.n_rows + TP - 1) / TP);   // the host refuses more than INT_MAX tiles
+    my_tiles = (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  }
   const int L = a.n_layer;
 
   if (warp == kProducerWarp) {
@@ -470,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
         bulk_g2s(sbase + OFF_W + stage * WBLK_BYTES, src, WBLK_BYTES, full0 + 8 * stage);
         if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
       };
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+      for (int it = 0; it < my_tiles; ++it)
         for (int step = 0; step < a.n_steps; ++step) {
           put_block(a.ioblocks);
           for (int l = 0; l < L; ++l) {
@@ -580,7 +597,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       umma_ts(tb + COL_O + 24 * h, tb + pcol + 8 * TP, desc_lo(sbase + OFF_SIDE + 2 * SIDE_BYTES + 3 * h * SIDE_LBO, 128), desc_hi(SIDE_LBO), kN32Mn, 1u,
               leader);
     };
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+    for (int it = 0; it < my_tiles; ++it)
       for (int step = 0; step < a.n_steps; ++step) {
         uint32_t wa;
         // 0. x = [x_t | T1 x_t | T2 x_t] Win + b at hi/lo precision: A = block 0 chunk columns 0..5 (hi, lo, hi),
@@ -700,9 +717,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     uint8_t* const side1 = side0 ? side0 + SIDE_BYTES : nullptr;
     uint8_t* const side2 = side0 ? side0 + 2 * SIDE_BYTES : nullptr;
 
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const long g0 = (long)tile * TP;
-      const int npose = (int)min((long)TP, a.n_rows - g0);
+    float macc = 0.f;     // mean_over_hyp: running hypothesis sum of output element `tid` of the pose being completed
+    for (int it = 0; it < my_tiles; ++it) {
+      const long g0 = a.mean_over_hyp ? row_lo + (long)it * TP : ((long)blockIdx.x + (long)it * gridDim.x) * TP;
+      const int npose = (int)min((long)TP, (a.mean_over_hyp ? row_hi : a.n_rows) - g0);
       const int ci = a.c_in, co = a.c_out;
       const int nin = npose * NP * ci, nval = npose * NP * co;  // valid (pose, joint, coordinate) triples: input, output
       for (int idx = tid; idx < TM * XS; idx += kComputeThreads) xt[idx] = 0.f;
@@ -710,7 +728,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       for (int idx = tid; idx < nin; idx += kComputeThreads) {
         const int p = idx / (NP * ci), rem = idx - p * (NP * ci);
         const long g = g0 + p;
-        const long src = a.x_is_repeated ? g : (g % a.n_pose);
+        long src;
+        if (a.mean_over_hyp) { const long b = g / a.n_hyp; src = a.x_is_repeated ? (g - b * a.n_hyp) * a.n_pose + b : b; }
+        else src = a.x_is_repeated ? g : (g % a.n_pose);
         xt[(p * PS + rem / ci) * XS + rem % ci] = a.x_in[src * (NP * ci) + rem];
       }
       bar_compute();
@@ -903,7 +923,9 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
 #pragma unroll
               for (int k = 0; k < 3; ++k) et[k] = fmaf(cf.y, u[10 + k], fmaf(cf.x, u[5 + k], et[k]));
             }
-            const size_t o = ((size_t)(g0 + p) * NP + i) * co;
+            long grow = g0 + p;       // row of the caller's hypothesis-major arrays (noise, eps)
+            if (a.mean_over_hyp) { const long b = grow / a.n_hyp; grow = (grow - b * a.n_hyp) * a.n_pose + b; }
+            const size_t o = ((size_t)grow * NP + i) * co;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
               const int n = n0 + k;
@@ -926,7 +948,21 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           signal_ready(c);
         }
       }
-      if (!a.forward_only) {
+      if (a.mean_over_hyp) {
+        // mean(reshape(H, -1, 17, c), 0) fused into the store: the rows of this CTA are pose-major, so thread e < 17 c walks
+        // the tile's rows in order, carries the running sum of its element across tiles in a register and stores a pose
+        // when its last hypothesis has passed (same summation order and division as hyp_mean_kernel: bit-identical)
+        if (tid < NP * co) {
+          const float* src = xt + (tid / co) * XS + tid % co;
+          for (int p = 0; p < npose; ++p) {
+            const long g = g0 + p, b = g / a.n_hyp;
+            const int h = (int)(g - b * a.n_hyp);
+            const float v = src[p * PS * XS];
+            macc = h == 0 ? __fadd_rn(0.f, v) : __fadd_rn(macc, v);
+            if (h == a.n_hyp - 1) a.out[(size_t)b * NP * co + tid] = __fdiv_rn(macc, (float)a.n_hyp);
+          }
+        }
+      } else if (!a.forward_only) {
         for (int idx = tid; idx < nval; idx += kComputeThreads) {
           const int p = idx / (NP * co), rem = idx - p * (NP * co);
           a.out[(size_t)g0 * NP * co + idx] = xt[(p * PS + rem / co) * XS + rem % co];
@@ -1135,7 +1171,8 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
   a.trace = m->trace; a.trace_cap = m->trace_cap;
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   if (n_tiles > 0x7fffffffL) { set_error("tensor-core engine: more than 2^31 tiles of 7 poses in one call"); return DP_ERR_INVALID; }
-  const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
+  int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
+  if (a.mean_over_hyp) grid = (int)(a.n_pose < m->sm_count ? a.n_pose : m->sm_count);   // CTAs own whole poses
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
   cudaLaunchAttribute attr[1];
@@ -1152,10 +1189,11 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
 
 int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
                const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
-               const unsigned char* mask, cudaStream_t s) {
+               const unsigned char* mask, int mean_over_hyp, cudaStream_t s) {
   Tc2Args a{};
   a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
-  a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_steps = n_steps; a.noise = noise; a.mask = mask;
+  a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_hyp = n_hyp; a.mean_over_hyp = (mean_over_hyp && n_hyp > 1) ? 1 : 0;
+  a.n_steps = n_steps; a.noise = noise; a.mask = mask;
   a.steps_dev = steps_dev; a.forward_only = 0;
   return tc2_launch(m, a, inl, s);
 }
@@ -1170,7 +1208,7 @@ int tc2_forward(dp_model* m, const float* x, const float* t, const unsigned char
     if (d.has_temb) DP_TRY(simt_temb(m, t + o, 1, nullptr, nn, s));
     Tc2Args a{};
     a.x_in = x + (size_t)o * d.n_pts * d.c_in; a.x_is_repeated = 1; a.out = out + (size_t)o * d.n_pts * d.c_out;
-    a.n_rows = nn; a.n_pose = nn; a.n_steps = 1; a.noise = nullptr; a.mask = mask; a.steps_dev = nullptr; a.forward_only = 1;
+    a.n_rows = nn; a.n_pose = nn; a.n_hyp = 1; a.n_steps = 1; a.noise = nullptr; a.mask = mask; a.steps_dev = nullptr; a.forward_only = 1;
     DP_TRY(tc2_launch(m, a, &none, s));
   }
   return DP_OK;

@@ -1,0 +1,911 @@
+// Split-precision tensor-core engine ("tcx"): the ACCURATE tcgen05 path.  Persistent sm_100a kernel, one 128-row tile
+// (7 poses x 17 joints) per CTA, every layer (and, for the sampler, every DDIM step) executed without leaving the SM.
+//
+// Why it exists: the default engine (dp_tc2.cu) rounds every tensor-core operand to fp16 (11-bit significand).  Behind a
+// DDIM schedule that error is damped (x_T within 1e-3 of the fp32 reference), but a plain forward call -- GCNdiff.forward
+// used for a loss, and above all the GCNpose lifter whose output IS the xyz handed to the sampler -- carries it undamped:
+// ~7e-4 relative, 2e-3 abs on random weights (oracle/tc_emulation.py).  Emulating the rounding points one class at a
+// time shows that every class matters (activations, weights, attention probabilities, graph operands): only splitting
+// all of them brings the lifter to 3e-6.  So this engine
+//
+//   * runs the dense projections (QKV, out-proj, GraphNet fc1/fc2, both Chebyshev convolutions: 11.0 of the 12.3 MMAC
+//     per pose-forward) on tcgen05 as THREE fp16 products per K step, D += A_hi W_hi + A_lo W_hi + A_hi W_lo with
+//     A = A_hi + A_lo and W = W_hi + W_lo split into fp16 pairs (~22 significand bits each, fp32 accumulation in TMEM);
+//   * keeps everything else in fp32 on the CUDA cores, in shared memory: LayerNorm (unbiased std, eps on std), the
+//     per-head attention with its softmax (q straight from TMEM, k and v as fp32 rows), the 17x17 graph operators
+//     (Chebyshev T1/T2 over the neighbour lists, learnable-adjacency L^), the residual stream, the 5-wide input/output
+//     convolutions and the DDIM update.
+//
+// It serves dp_forward for both model kinds (GCNdiff with per-sample timesteps, GCNpose uv -> xyz, optionally fused with
+// the runner's root-centring + concat into uvxyz, runners/diffpose_frame.py:337-343) and is selectable for the sampler.
+// Result: <= 2e-5 from the fp32 oracle (tests/test_gpu_tc.py) at ~8x the speed of the fp32 FMA engine.
+//
+// Reference semantics: see the list at the top of dp_simt.cu (same functions, same file:line).
+#include <cuda_fp16.h>
+#include <cmath>
+#include "dp_internal.h"
+#include "dp_sm100.cuh"
+
+namespace dp {
+
+namespace {
+
+using namespace sm100;
+
+constexpr int NP = 17;
+constexpr int TM = 128;              // tile rows = UMMA M
+constexpr int TP = 7;                // poses per tile
+constexpr int TR = TP * NP;          // 119 valid rows (row = pose * 17 + joint)
+constexpr int H = 96;
+constexpr int XLD = 100;             // fp32 row stride (floats): thread-per-row float4 access is conflict free
+constexpr int NSTAGE = 3;
+constexpr int WK = 112;              // weight block K extent: 96 weights + 16 (bias slab; k=96 hi, k=97 lo)
+constexpr int W_LBO = 12 * 128;      // bytes between K-adjacent 8x8 core matrices of a weight block
+constexpr int W_SBO = 128;           // bytes between N-adjacent core matrices
+constexpr int WBLK_BYTES = (WK / 8) * W_LBO;        // 21504
+constexpr int A_LBO = 16 * 128 + 16; // 2064: +16 B skews consecutive K chunks across banks
+constexpr int A_SBO = 128;
+constexpr int ABLK_BYTES = 12 * A_LBO;              // 24768
+constexpr int PAIR_BYTES = 2 * ABLK_BYTES;          // an operand = (hi block, lo block)
+constexpr int ONES_BYTES = 2 * A_LBO;               // 4128
+constexpr int BLOCKS_PER_LAYER = 14;                // each one a (hi, lo) pair of ring entries
+constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
+constexpr int kComputeThreads = 256;
+constexpr int kThreads = kComputeThreads + 32;
+constexpr int TMEM_COLS = 512;
+constexpr int XS = 8;                // x_t / eps row stride (floats)
+
+// shared memory map (bytes)
+constexpr int al16(int x) { return (x + 15) / 16 * 16; }
+constexpr int al128(int x) { return (x + 127) / 128 * 128; }
+constexpr int OFF_X = 0;                                   // fp32 residual stream [119][100]
+constexpr int OFF_P0 = al128(OFF_X + TR * XLD * 4);        // operand pair 0 (hi, lo); aliased by the fp32 buffer S0 [119][100]
+constexpr int OFF_P1 = OFF_P0 + al128(PAIR_BYTES);         // operand pair 1; aliased by the fp32 buffer S1
+constexpr int OFF_ONES = OFF_P1 + al128(PAIR_BYTES);       // constant-one K slab (the bias rides in the MMA)
+constexpr int OFF_W = al128(OFF_ONES + ONES_BYTES);        // weight ring
+constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][8] fp32
+constexpr int OFF_EP = OFF_XT + TM * XS * 4;               // eps [128][8] fp32
+constexpr int OFF_NBI = OFF_EP + TM * XS * 4;              // neighbour index  [17][9] int
+constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
+constexpr int OFF_LH = al16(OFF_NBC + NP * NNB * 8);       // L^ [17][17]
+constexpr int OFF_TE = al16(OFF_LH + NP * NP * 4);         // temb rows of the current layer: [7][96] (forward) or [96] (sampler)
+constexpr int OFF_MASK = OFF_TE + TP * H * 4;              // key mask [32]
+constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[3], empty[3], done
+constexpr int OFF_TMEM = OFF_BAR + 128;
+constexpr int SMEM_BYTES = OFF_TMEM + 16;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
+static_assert(TR * XLD * 4 <= PAIR_BYTES, "an fp32 buffer must fit the operand pair it aliases");
+static_assert(OFF_W % 128 == 0 && OFF_P0 % 128 == 0 && OFF_P1 % 128 == 0 && OFF_ONES % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 &&
+              OFF_XT % 16 == 0 && OFF_TE % 16 == 0, "alignment");
+
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24
+constexpr uint32_t kIdescN96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
+
+// byte offset of the 16-byte chunk holding elements (row, 8*kc .. 8*kc+7) inside an fp16 operand block
+__device__ __forceinline__ uint32_t a_chunk(int row, int kc) { return kc * A_LBO + (row >> 3) * A_SBO + (row & 7) * 16; }
+
+// v[0..8) = hi + lo, both fp16 -> chunk (row, kc) of the hi and the lo block of an operand pair
+__device__ __forceinline__ void store_split(uint8_t* pair, int row, int kc, const float* v) {
+  uint4 hi, lo;
+  split8(v, hi, lo);
+  *reinterpret_cast<uint4*>(pair + a_chunk(row, kc)) = hi;
+  *reinterpret_cast<uint4*>(pair + ABLK_BYTES + a_chunk(row, kc)) = lo;
+}
+// rows 119..127 of an operand: any finite value (their accumulator rows are never read)
+__device__ __forceinline__ void store_zero(uint8_t* pair, int row, int kc) {
+  *reinterpret_cast<uint4*>(pair + a_chunk(row, kc)) = make_uint4(0, 0, 0, 0);
+  *reinterpret_cast<uint4*>(pair + ABLK_BYTES + a_chunk(row, kc)) = make_uint4(0, 0, 0, 0);
+}
+
+struct TcxArgs {
+  const Weights* w;          // fp32 blob (LayerNorm, L^, b2, in/out convolutions)
+  const uint8_t* wpack;      // fp16 weight blocks [n_layer][14][2 (hi, lo)][21504 B]
+  int n_layer;
+  int c_in, c_out;           // coordinate widths (<= 5): uvxyz -> uvxyz for GCNdiff, uv -> xyz for GCNpose
+  int forward_only;          // 1: a single denoiser / lifter forward (dp_forward); 0: the DDIM loop
+  int has_temb;
+  int emit_uvxyz;            // forward_only GCNpose: write [uv | xyz - xyz_root] (5 wide) instead of xyz (dp_lift)
+  const float* x_in;
+  int x_is_repeated;
+  float* out;
+  long n_rows, n_pose;
+  int n_steps;
+  const float* temb;         // sampler: [n_steps][n_layer][96]; forward: [n_rows][n_layer][96]
+  const float* noise;
+  const unsigned char* mask;
+  const dp_step* steps_dev;
+};
+
+struct Pipe {
+  uint32_t full0, empty0, done;   // smem addresses of the barriers
+  uint32_t stage, phase;          // weight ring position (thread 0 and the producer keep their own copy)
+  uint32_t done_phase;            // every compute thread tracks the parity of the "GEMM finished" barrier
+};
+
+// D[:, 0..96) (+)= A W^T (+ bias) at split precision: A = operand pair (hi, lo), W = two consecutive ring entries (hi with
+// the bias slab, lo).  Largest terms first.  Issued by a single thread.
+__device__ __forceinline__ void issue_gemm(Pipe& p, uint32_t smem_base, uint32_t tmem_d, int pair_off, bool accumulate, bool bias) {
+  const uint32_t ah = smem_base + pair_off, al = ah + ABLK_BYTES;
+  mbar_wait(p.full0 + 8 * p.stage, p.phase);
+  tc_fence_after();
+  uint32_t wa = smem_base + OFF_W + p.stage * WBLK_BYTES;
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks)
+    umma_f16(tmem_d, make_desc(ah + ks * 2 * A_LBO, A_LBO, A_SBO), make_desc(wa + ks * 2 * W_LBO, W_LBO, W_SBO), kIdescN96,
+             (accumulate || ks > 0) ? 1u : 0u);
+  if (bias)
+    umma_f16(tmem_d, make_desc(smem_base + OFF_ONES, A_LBO, A_SBO), make_desc(wa + 12 * W_LBO, W_LBO, W_SBO), kIdescN96, 1u);
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks)
+    umma_f16(tmem_d, make_desc(al + ks * 2 * A_LBO, A_LBO, A_SBO), make_desc(wa + ks * 2 * W_LBO, W_LBO, W_SBO), kIdescN96, 1u);
+  umma_commit(p.empty0 + 8 * p.stage);   // the stage is free once these MMAs have read it
+  if (++p.stage == NSTAGE) { p.stage = 0; p.phase ^= 1; }
+  mbar_wait(p.full0 + 8 * p.stage, p.phase);
+  tc_fence_after();
+  wa = smem_base + OFF_W + p.stage * WBLK_BYTES;
+#pragma unroll
+  for (int ks = 0; ks < 6; ++ks)
+    umma_f16(tmem_d, make_desc(ah + ks * 2 * A_LBO, A_LBO, A_SBO), make_desc(wa + ks * 2 * W_LBO, W_LBO, W_SBO), kIdescN96, 1u);
+  umma_commit(p.empty0 + 8 * p.stage);
+  if (++p.stage == NSTAGE) { p.stage = 0; p.phase ^= 1; }
+}
+
+// after an operand was written with ordinary stores: make it visible to the tensor core (async proxy), then sync
+__device__ __forceinline__ void publish_operand() {
+  fence_async_smem();
+  tc_fence_before();
+  bar_compute();
+}
+__device__ __forceinline__ void wait_gemm(Pipe& p) {
+  mbar_wait(p.done, p.done_phase);
+  p.done_phase ^= 1;
+  tc_fence_after();
+}
+
+// Epilogues: warp w reads TMEM lanes 32*(w&3).. (its rows) and the column half (w>>2) of a 96-column accumulator.
+enum EpiKind { EPI_F32 = 0, EPI_XADD = 1, EPI_XADD_RELU = 2, EPI_RELU_SPLIT = 3, EPI_RELU_TEMB_F32 = 4 };
+
+template <int KIND>
+__device__ __forceinline__ void epilogue(uint8_t* smem, uint32_t tmem_acc, int dst_off, const float* __restrict__ temb_rows, int temb_stride) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = (warp & 3) * 32 + lane;
+  const int c0 = (warp >> 2) * 48;
+  const uint32_t taddr = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll
+  for (int cc = 0; cc < 48; cc += 16) {
+    const int c = c0 + cc;
+    float v[16];
+    tmem_ld16(taddr + c, v);     // (warp-collective: every lane takes part, valid row or not)
+    if (KIND == EPI_XADD_RELU || KIND == EPI_RELU_SPLIT || KIND == EPI_RELU_TEMB_F32) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    }
+    if (KIND == EPI_RELU_SPLIT) {
+      uint8_t* pair = smem + dst_off;
+      if (row < TR) { store_split(pair, row, c >> 3, v); store_split(pair, row, (c >> 3) + 1, v + 8); }
+      else { store_zero(pair, row, c >> 3); store_zero(pair, row, (c >> 3) + 1); }
+      continue;
+    }
+    if (row >= TR) continue;
+    if (KIND == EPI_RELU_TEMB_F32 && temb_rows != nullptr) {
+      const float* te = temb_rows + (row / NP) * temb_stride + c;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        const float4 t = *reinterpret_cast<const float4*>(te + i);
+        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
+      }
+    }
+    if (KIND == EPI_XADD || KIND == EPI_XADD_RELU) {
+      float* X = reinterpret_cast<float*>(smem + OFF_X) + row * XLD + c;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) {
+        float4 x = *reinterpret_cast<float4*>(X + i);
+        x.x += v[i]; x.y += v[i + 1]; x.z += v[i + 2]; x.w += v[i + 3];
+        *reinterpret_cast<float4*>(X + i) = x;
+      }
+    } else {   // fp32 rows into a scratch buffer
+      float* Z = reinterpret_cast<float*>(smem + dst_off) + row * XLD + c;
+#pragma unroll
+      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(Z + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+  }
+}
+
+// LayerNorm of the residual stream (GraFormer.py:67-70: unbiased std, eps added to std): lanes (2r, 2r+1) own the two
+// 48-channel halves of row r.  TO_OPERAND: split into the operand pair at dst_off; else fp32 rows at dst_off.
+template <bool TO_OPERAND>
+__device__ __forceinline__ void layer_norm_tile(uint8_t* smem, int dst_off, const float* __restrict__ ga, const float* __restrict__ gb) {
+  const int row = threadIdx.x >> 1, hh = threadIdx.x & 1;
+  const float* xr = reinterpret_cast<const float*>(smem + OFF_X) + min(row, TR - 1) * XLD + hh * 48;
+  float v[48];
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const float4 u = *reinterpret_cast<const float4*>(xr + 4 * q);
+    v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
+  }
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 48; ++i) s += v[i];
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  const float mean = s * (1.0f / (float)H);
+  float q2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 48; ++i) { v[i] -= mean; q2 = fmaf(v[i], v[i], q2); }
+  q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+  const float inv = 1.0f / (sqrtf(q2 * (1.0f / (float)(H - 1))) + 1e-6f);
+  if (row >= TR) {
+    if (TO_OPERAND) {
+#pragma unroll
+      for (int c = 0; c < 6; ++c) store_zero(smem + dst_off, row, hh * 6 + c);
+    }
+    return;
+  }
+#pragma unroll
+  for (int q = 0; q < 12; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(ga + hh * 48) + q), b = __ldg(reinterpret_cast<const float4*>(gb + hh * 48) + q);
+    v[4 * q] = fmaf(a.x * inv, v[4 * q], b.x); v[4 * q + 1] = fmaf(a.y * inv, v[4 * q + 1], b.y);
+    v[4 * q + 2] = fmaf(a.z * inv, v[4 * q + 2], b.z); v[4 * q + 3] = fmaf(a.w * inv, v[4 * q + 3], b.w);
+  }
+  if (TO_OPERAND) {
+#pragma unroll
+    for (int c = 0; c < 6; ++c) store_split(smem + dst_off, row, hh * 6 + c, v + 8 * c);
+  } else {
+    float* y = reinterpret_cast<float*>(smem + dst_off) + row * XLD + hh * 48;
+#pragma unroll
+    for (int q = 0; q < 12; ++q) *reinterpret_cast<float4*>(y + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+  }
+}
+
+// Multi-head attention over the joints of each pose (GraFormer.py:99-113) in fp32.  q: this thread's row straight from
+// the accumulator columns [0, 96) in TMEM; k, v: fp32 rows in S0 / S1.  One thread per (row, head pair): warp w owns rows
+// 32*(w&3).. and heads 2*(w>>2), 2*(w>>2)+1.  The outputs stay in registers until every thread has finished reading v
+// (S1 aliases the operand pair the result is written to).
+__device__ __forceinline__ void attention_tile(uint8_t* smem, uint32_t tmem_base, int out_pair_off) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = (warp & 3) * 32 + lane;
+  const int h0 = (warp >> 2) * 2;
+  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  const float* maskf = reinterpret_cast<const float*>(smem + OFF_MASK);
+  const float* K = reinterpret_cast<const float*>(smem + OFF_P0);
+  const float* V = reinterpret_cast<const float*>(smem + OFF_P1);
+  const float scale = 1.0f / sqrtf(24.0f);
+  const int p = min(row, TR - 1) / NP;
+  float o[48];
+#pragma unroll
+  for (int hl = 0; hl < 2; ++hl) {
+    const int h = h0 + hl;
+    float q[24];
+    {
+      float a[16], b[16];
+      tmem_ld16_async(taddr + 24 * h, a);
+      tmem_ld16_async(taddr + 24 * h + 8, b);
+      tmem_ld_wait();
+      launder<16>(a);
+      launder<16>(b);
+#pragma unroll
+      for (int i = 0; i < 16; ++i) q[i] = a[i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[16 + i] = b[8 + i];
+    }
+    float sc[NP];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float* kr = K + (p * NP + j) * XLD + 24 * h;
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const float4 kv = *reinterpret_cast<const float4*>(kr + 4 * c);
+        s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s); s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
+      }
+      s = s * scale;
+      if (maskf[j] == 0.f) s = -1e9f;
+      sc[j] = s;
+      mx = fmaxf(mx, s);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+    const float inv = 1.0f / sum;
+    float* oh = o + 24 * hl;
+#pragma unroll
+    for (int e = 0; e < 24; ++e) oh[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float* vr = V + (p * NP + j) * XLD + 24 * h;
+      const float pj = sc[j] * inv;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c);
+        oh[4 * c] = fmaf(pj, vv.x, oh[4 * c]); oh[4 * c + 1] = fmaf(pj, vv.y, oh[4 * c + 1]);
+        oh[4 * c + 2] = fmaf(pj, vv.z, oh[4 * c + 2]); oh[4 * c + 3] = fmaf(pj, vv.w, oh[4 * c + 3]);
+      }
+    }
+  }
+  tc_fence_before();
+  bar_compute();               // everybody is done with k and v
+  uint8_t* pair = smem + out_pair_off;
+#pragma unroll
+  for (int c = 0; c < 6; ++c) {
+    if (row < TR) store_split(pair, row, 3 * h0 + c, o + 8 * c);
+    else store_zero(pair, row, 3 * h0 + c);
+  }
+}
+
+// out[i] = sum_j L^[i][j] Y[j] over the pose of row i (GraFormer.py:174-186), Y fp32 rows at src_off -> operand pair
+__device__ __forceinline__ void lhat_to_operand(uint8_t* smem, int src_off, int pair_off) {
+  const int row = threadIdx.x & 127;
+  uint8_t* pair = smem + pair_off;
+  if (row >= TR) {
+    for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) store_zero(pair, row, kc);
+    return;
+  }
+  const float* Y = reinterpret_cast<const float*>(smem + src_off);
+  const float* lh = reinterpret_cast<const float*>(smem + OFF_LH);
+  const int p = row / NP, i = row - p * NP;
+  float co[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) co[j] = lh[i * NP + j];
+  for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float* src = Y + (p * NP + j) * XLD + kc * 8;
+      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] = fmaf(co[j], u0.x, acc[0]); acc[1] = fmaf(co[j], u0.y, acc[1]); acc[2] = fmaf(co[j], u0.z, acc[2]); acc[3] = fmaf(co[j], u0.w, acc[3]);
+      acc[4] = fmaf(co[j], u1.x, acc[4]); acc[5] = fmaf(co[j], u1.y, acc[5]); acc[6] = fmaf(co[j], u1.z, acc[6]); acc[7] = fmaf(co[j], u1.w, acc[7]);
+    }
+    store_split(pair, row, kc, acc);
+  }
+}
+
+// X[i] += sum_j L^[i][j] Z[j] + b2   (second LAM_Gconv with fc2 commuted in front of the aggregation), Z fp32 rows at src_off
+__device__ __forceinline__ void lhat_residual(uint8_t* smem, int src_off, const float* __restrict__ b2) {
+  const int row = threadIdx.x & 127;
+  if (row >= TR) return;
+  const float* Z = reinterpret_cast<const float*>(smem + src_off);
+  float* X = reinterpret_cast<float*>(smem + OFF_X) + row * XLD;
+  const float* lh = reinterpret_cast<const float*>(smem + OFF_LH);
+  const int p = row / NP, i = row - p * NP;
+  float co[NP];
+#pragma unroll
+  for (int j = 0; j < NP; ++j) co[j] = lh[i * NP + j];
+  for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+    float acc[8];
+    const float4 bb0 = __ldg(reinterpret_cast<const float4*>(b2 + kc * 8)), bb1 = __ldg(reinterpret_cast<const float4*>(b2 + kc * 8 + 4));
+    acc[0] = bb0.x; acc[1] = bb0.y; acc[2] = bb0.z; acc[3] = bb0.w; acc[4] = bb1.x; acc[5] = bb1.y; acc[6] = bb1.z; acc[7] = bb1.w;
+#pragma unroll
+    for (int j = 0; j < NP; ++j) {
+      const float* src = Z + (p * NP + j) * XLD + kc * 8;
+      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
+      acc[0] = fmaf(co[j], u0.x, acc[0]); acc[1] = fmaf(co[j], u0.y, acc[1]); acc[2] = fmaf(co[j], u0.z, acc[2]); acc[3] = fmaf(co[j], u0.w, acc[3]);
+      acc[4] = fmaf(co[j], u1.x, acc[4]); acc[5] = fmaf(co[j], u1.y, acc[5]); acc[6] = fmaf(co[j], u1.z, acc[6]); acc[7] = fmaf(co[j], u1.w, acc[7]);
+    }
+    float4 x0 = *reinterpret_cast<float4*>(X + kc * 8), x1 = *reinterpret_cast<float4*>(X + kc * 8 + 4);
+    x0.x += acc[0]; x0.y += acc[1]; x0.z += acc[2]; x0.w += acc[3]; x1.x += acc[4]; x1.y += acc[5]; x1.z += acc[6]; x1.w += acc[7];
+    *reinterpret_cast<float4*>(X + kc * 8) = x0;
+    *reinterpret_cast<float4*>(X + kc * 8 + 4) = x1;
+  }
+}
+
+// One part of the Chebyshev input panel [V | T1 V | T2 V] (ChebConv.py:74-112) as a split operand pair; V = fp32 rows at
+// src_off.  ORDER 0: V itself, 1: T1 V, 2: T2 V (fp32 over the neighbour list).  ORDER 12: T1 V -> pair_off and T2 V ->
+// pair_off2 in one pass over the neighbours.
+template <int ORDER>
+__device__ __forceinline__ void cheb_part(uint8_t* smem, int src_off, int pair_off, int pair_off2 = 0) {
+  const int row = threadIdx.x & 127;
+  uint8_t* pair = smem + pair_off;
+  uint8_t* pair2 = smem + pair_off2;
+  if (row >= TR) {
+    for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+      store_zero(pair, row, kc);
+      if (ORDER == 12) store_zero(pair2, row, kc);
+    }
+    return;
+  }
+  const float* V = reinterpret_cast<const float*>(smem + src_off);
+  if (ORDER == 0) {
+    for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+      const float* src = V + row * XLD + kc * 8;
+      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
+      const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+      store_split(pair, row, kc, u);
+    }
+    return;
+  }
+  const int* nbi = reinterpret_cast<const int*>(smem + OFF_NBI);
+  const float2* nbc = reinterpret_cast<const float2*>(smem + OFF_NBC);
+  const int p = row / NP, i = row - p * NP;
+  int nj[NNB];
+  float2 nc[NNB];
+#pragma unroll
+  for (int n = 0; n < NNB; ++n) { nj[n] = p * NP + nbi[i * NNB + n]; nc[n] = nbc[i * NNB + n]; }
+  for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+    float a1[8], a2[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { a1[e] = 0.f; a2[e] = 0.f; }
+#pragma unroll
+    for (int n = 0; n < NNB; ++n) {
+      const float* src = V + nj[n] * XLD + kc * 8;
+      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
+      const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        if (ORDER == 1 || ORDER == 12) a1[e] = fmaf(nc[n].x, u[e], a1[e]);
+        if (ORDER == 2 || ORDER == 12) a2[e] = fmaf(nc[n].y, u[e], a2[e]);
+      }
+    }
+    if (ORDER == 1) store_split(pair, row, kc, a1);
+    else if (ORDER == 2) store_split(pair, row, kc, a2);
+    else { store_split(pair, row, kc, a1); store_split(pair2, row, kc, a2); }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg inl) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  float* X = reinterpret_cast<float*>(smem + OFF_X);
+  float* xt = reinterpret_cast<float*>(smem + OFF_XT);
+  float* ep = reinterpret_cast<float*>(smem + OFF_EP);
+  float* lh = reinterpret_cast<float*>(smem + OFF_LH);
+  float* te = reinterpret_cast<float*>(smem + OFF_TE);
+  float* maskf = reinterpret_cast<float*>(smem + OFF_MASK);
+  int* nbi = reinterpret_cast<int*>(smem + OFF_NBI);
+  float2* nbc = reinterpret_cast<float2*>(smem + OFF_NBC);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + OFF_TMEM);
+  const Weights& w = *a.w;
+
+  Pipe pp;
+  pp.full0 = sbase + OFF_BAR; pp.empty0 = sbase + OFF_BAR + 32; pp.done = sbase + OFF_BAR + 64;
+  pp.stage = 0; pp.phase = 0; pp.done_phase = 0;
+
+  // ---------------------------------------------------------------- one-time setup
+  if (tid == 0) {
+    for (int s = 0; s < NSTAGE; ++s) { mbar_init(pp.full0 + 8 * s, 1); mbar_init(pp.empty0 + 8 * s, 1); }
+    mbar_init(pp.done, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 0) tmem_alloc(sbase + OFF_TMEM, TMEM_COLS);
+  // constant-one K slab: element (row, 0) = (row, 1) = 1, the other 14 of the 16 columns are 0
+  for (int i = tid; i < 2 * TM; i += kThreads) {
+    const int row = i & 127, kc = i >> 7;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (kc == 0) v.x = pack2(1.0f, 1.0f);
+    *reinterpret_cast<uint4*>(smem + OFF_ONES + a_chunk(row, kc)) = v;
+  }
+  if (tid < 32) maskf[tid] = (tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f;
+  if (tid < NP) {
+    // neighbour list of joint tid: columns where T1 or T2 is non-zero, padded with (self, 0, 0)
+    int n = 0;
+    for (int j = 0; j < NP; ++j) {
+      const float c1 = __ldg(w.t1 + tid * NP + j), c2 = __ldg(w.t2 + tid * NP + j);
+      if ((c1 != 0.f || c2 != 0.f) && n < NNB) { nbi[tid * NNB + n] = j; nbc[tid * NNB + n] = make_float2(c1, c2); ++n; }
+    }
+    for (; n < NNB; ++n) { nbi[tid * NNB + n] = tid; nbc[tid * NNB + n] = make_float2(0.f, 0.f); }
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const long n_tiles = (a.n_rows + TP - 1) / TP;
+  const int L = a.n_layer;
+  const int ci = a.c_in, co = a.c_out;
+
+  if (warp == 8) {
+    // ---------------------------------------------------------------- weight producer (TMA bulk copies): the (hi, lo) blocks
+    // of a layer in the order the kernel consumes them
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x)
+        for (int step = 0; step < a.n_steps; ++step)
+          for (int blk = 0; blk < L * BLOCKS_PER_LAYER * 2; ++blk) {
+            mbar_wait_sleep(pp.empty0 + 8 * stage, phase ^ 1);
+            mbar_expect_tx(pp.full0 + 8 * stage, WBLK_BYTES);
+            bulk_g2s(sbase + OFF_W + stage * WBLK_BYTES, a.wpack + (size_t)blk * WBLK_BYTES, WBLK_BYTES, pp.full0 + 8 * stage);
+            if (++stage == NSTAGE) { stage = 0; phase ^= 1; }
+          }
+    }
+    __syncwarp();
+  } else {
+    // ---------------------------------------------------------------- compute warps
+    for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const long g0 = tile * TP;
+      const int npose = (int)min((long)TP, a.n_rows - g0);
+      const int R = npose * NP;
+      for (int idx = tid; idx < TM * XS; idx += kComputeThreads) {
+        const int r = idx >> 3, c = idx & 7;
+        float v = 0.f;
+        if (r < R && c < ci) {
+          const long g = g0 + r / NP;
+          const long src = a.x_is_repeated ? g : (g % a.n_pose);
+          v = a.x_in[(src * NP + (r % NP)) * ci + c];
+        }
+        xt[idx] = v;
+      }
+      bar_compute();
+
+      for (int step = 0; step < a.n_steps; ++step) {
+        // ---- input ChebConv (K = 3 c_in <= 15): fp32 on the CUDA cores.  B[row][order * c_in + c] = (T_order x)[row][c]
+        float* Bin = reinterpret_cast<float*>(smem + OFF_P0);   // [128][16]
+        for (int idx = tid; idx < TM * ci; idx += kComputeThreads) {
+          const int r = idx / ci, c = idx - r * ci;
+          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+          if (r < TR) {
+            const int p = r / NP, i = r - p * NP;
+            v0 = xt[r * XS + c];
+#pragma unroll
+            for (int n = 0; n < NNB; ++n) {
+              const float u = xt[(p * NP + nbi[i * NNB + n]) * XS + c];
+              const float2 cf = nbc[i * NNB + n];
+              v1 = fmaf(cf.x, u, v1);
+              v2 = fmaf(cf.y, u, v2);
+            }
+          }
+          Bin[r * 16 + c] = v0; Bin[r * 16 + ci + c] = v1; Bin[r * 16 + 2 * ci + c] = v2;
+        }
+        bar_compute();
+        {
+          const int row = tid & 127, hh = tid >> 7;
+          if (row < TR) {
+            float acc[48];
+#pragma unroll
+            for (int g = 0; g < 12; ++g) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.bin + hh * 48) + g);
+              acc[4 * g] = b4.x; acc[4 * g + 1] = b4.y; acc[4 * g + 2] = b4.z; acc[4 * g + 3] = b4.w;
+            }
+            for (int k = 0; k < 3 * ci; ++k) {
+              const float bv = Bin[row * 16 + k];
+#pragma unroll
+              for (int g = 0; g < 12; ++g) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w.win + k * H + hh * 48) + g);
+                acc[4 * g] = fmaf(bv, w4.x, acc[4 * g]); acc[4 * g + 1] = fmaf(bv, w4.y, acc[4 * g + 1]);
+                acc[4 * g + 2] = fmaf(bv, w4.z, acc[4 * g + 2]); acc[4 * g + 3] = fmaf(bv, w4.w, acc[4 * g + 3]);
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < 12; ++g)
+              *reinterpret_cast<float4*>(X + row * XLD + hh * 48 + 4 * g) = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+          }
+        }
+        bar_compute();
+
+        for (int l = 0; l < L; ++l) {
+          const LayerW& Lw = w.layer[l];
+          for (int i = tid; i < NP * NP; i += kComputeThreads) lh[i] = __ldg(Lw.lhat + i);
+          if (a.has_temb) {
+            if (a.forward_only) {      // per-sample timesteps: one projected embedding row per pose
+              for (int i = tid; i < TP * H; i += kComputeThreads) {
+                const int p = i / H;
+                te[i] = p < npose ? __ldg(a.temb + ((size_t)(g0 + p) * L + l) * H + (i - p * H)) : 0.f;
+              }
+            } else if (tid < H) {
+              te[tid] = __ldg(a.temb + ((size_t)step * L + l) * H + tid);
+            }
+          }
+          // ======== x = x + attn(LN0(x))
+          layer_norm_tile<true>(smem, OFF_P1, Lw.ln0_a, Lw.ln0_b);
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base + 0, OFF_P1, false, true);     // Q
+            issue_gemm(pp, sbase, tmem_base + 96, OFF_P1, false, true);    // K
+            issue_gemm(pp, sbase, tmem_base + 192, OFF_P1, false, true);   // V
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          epilogue<EPI_F32>(smem, tmem_base + 96, OFF_P0, nullptr, 0);     // k -> S0
+          epilogue<EPI_F32>(smem, tmem_base + 192, OFF_P1, nullptr, 0);    // v -> S1 (the GEMMs have finished reading pair 1)
+          tc_fence_before();
+          bar_compute();
+          attention_tile(smem, tmem_base, OFF_P0);                          // (syncs inside) -> pair 0
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, false, true);         // out projection
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          epilogue<EPI_XADD>(smem, tmem_base, 0, nullptr, 0);
+          tc_fence_before();
+          bar_compute();
+          // ======== x = x + GraphNet(LN1(x))
+          layer_norm_tile<false>(smem, OFF_P1, Lw.ln1_a, Lw.ln1_b);        // y -> S1
+          bar_compute();
+          lhat_to_operand(smem, OFF_P1, OFF_P0);                            // L^ y -> pair 0
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base + 0, OFF_P0, false, true);     // fc1, outputs 0..95
+            issue_gemm(pp, sbase, tmem_base + 96, OFF_P0, false, true);    // fc1, outputs 96..191
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          epilogue<EPI_RELU_SPLIT>(smem, tmem_base, OFF_P0, nullptr, 0);   // relu(h[:, 0:96]) -> pair 0
+          epilogue<EPI_RELU_SPLIT>(smem, tmem_base + 96, OFF_P1, nullptr, 0);   // relu(h[:, 96:192]) -> pair 1
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base + 192, OFF_P0, false, false);  // fc2, inputs 0..95
+            issue_gemm(pp, sbase, tmem_base + 192, OFF_P1, true, false);   // fc2, inputs 96..191
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          epilogue<EPI_F32>(smem, tmem_base + 192, OFF_P1, nullptr, 0);    // z -> S1
+          tc_fence_before();
+          bar_compute();
+          lhat_residual(smem, OFF_P1, Lw.b2);
+          bar_compute();
+          // ======== x = x + GC2(GC1(x) + temb)
+          cheb_part<0>(smem, OFF_X, OFF_P0);
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, false, true);
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          cheb_part<12>(smem, OFF_X, OFF_P0, OFF_P1);
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, true, false);
+            issue_gemm(pp, sbase, tmem_base, OFF_P1, true, false);
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          epilogue<EPI_RELU_TEMB_F32>(smem, tmem_base, OFF_P1, a.has_temb ? te : nullptr, a.forward_only ? H : 0);   // h1 -> S1
+          tc_fence_before();
+          bar_compute();
+          cheb_part<0>(smem, OFF_P1, OFF_P0);
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, false, true);
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          cheb_part<1>(smem, OFF_P1, OFF_P0);
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, true, false);
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          cheb_part<2>(smem, OFF_P1, OFF_P0);
+          publish_operand();
+          if (tid == 0) {
+            tc_fence_after();
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, true, false);
+            umma_commit(pp.done);
+          }
+          wait_gemm(pp);
+          epilogue<EPI_XADD_RELU>(smem, tmem_base, 0, nullptr, 0);
+          tc_fence_before();
+          bar_compute();
+        }
+
+        // ---- output ChebConv (N = c_out <= 5): U_k = X Wout_k on the CUDA cores, then eps = b + U0 + T1 U1 + T2 U2
+        {
+          float* U = reinterpret_cast<float*>(smem + OFF_P0);   // [2][128][16]
+          const int row = tid & 127, hh = tid >> 7;
+          float acc[15];
+#pragma unroll
+          for (int i = 0; i < 15; ++i) acc[i] = 0.f;
+          if (row < TR) {
+            for (int cq = 0; cq < 12; ++cq) {
+              const float4 xv = *reinterpret_cast<const float4*>(X + row * XLD + hh * 48 + cq * 4);
+              const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int c = hh * 48 + cq * 4 + e;
+#pragma unroll
+                for (int k3 = 0; k3 < 3; ++k3)
+#pragma unroll
+                  for (int n = 0; n < 5; ++n)
+                    if (n < co) acc[k3 * 5 + n] = fmaf(xs[e], __ldg(w.wout + (k3 * H + c) * co + n), acc[k3 * 5 + n]);
+              }
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 15; ++i) U[(hh * TM + row) * 16 + i] = acc[i];
+        }
+        bar_compute();
+        {
+          const float* U = reinterpret_cast<const float*>(smem + OFF_P0);
+          for (int idx = tid; idx < TR * co; idx += kComputeThreads) {
+            const int r = idx / co, n = idx - r * co;
+            const int p = r / NP, i = r - p * NP;
+            float v = __ldg(w.bout + n) + U[r * 16 + n] + U[(TM + r) * 16 + n];
+#pragma unroll
+            for (int q = 0; q < NNB; ++q) {
+              const int rj = p * NP + nbi[i * NNB + q];
+              const float2 cf = nbc[i * NNB + q];
+              v = fmaf(cf.x, U[rj * 16 + 5 + n] + U[(TM + rj) * 16 + 5 + n], v);
+              v = fmaf(cf.y, U[rj * 16 + 10 + n] + U[(TM + rj) * 16 + 10 + n], v);
+            }
+            ep[r * XS + n] = v;
+          }
+        }
+        bar_compute();
+        if (a.forward_only) {
+          if (a.emit_uvxyz) {
+            // the runner's glue (runners/diffpose_frame.py:337-343, with the intended out-of-place root-centring):
+            // [uv | xyz - xyz[root]] as the 5-wide input of the sampler
+            const int wd = ci + co;
+            for (int idx = tid; idx < R * wd; idx += kComputeThreads) {
+              const int r = idx / wd, n = idx - r * wd;
+              const int p = r / NP;
+              const float v = n < ci ? xt[r * XS + n] : __fsub_rn(ep[r * XS + (n - ci)], ep[(p * NP) * XS + (n - ci)]);
+              a.out[(size_t)g0 * NP * wd + idx] = v;
+            }
+          } else {
+            for (int idx = tid; idx < R * co; idx += kComputeThreads) a.out[(size_t)g0 * NP * co + idx] = ep[(idx / co) * XS + idx % co];
+          }
+        } else {
+          // ---- DDIM update (common/utils_diff.py:59-65), same operation order, no FMA contraction
+          const dp_step st = a.steps_dev ? a.steps_dev[step] : inl.s[step];
+          for (int idx = tid; idx < R * co; idx += kComputeThreads) {
+            const int r = idx / co, c = idx - r * co;
+            const float et = ep[r * XS + c], xv = xt[r * XS + c];
+            const float x0 = __fdiv_rn(__fsub_rn(xv, __fmul_rn(et, st.sqrt_1m_at)), st.sqrt_at);
+            float nx = __fmul_rn(st.sqrt_an, x0);
+            if (a.noise) {
+              const float z = a.noise[((size_t)step * a.n_rows + g0) * NP * co + idx];
+              nx = __fadd_rn(nx, __fmul_rn(st.c1, z));
+            }
+            xt[r * XS + c] = __fadd_rn(nx, __fmul_rn(st.c2, et));
+          }
+        }
+        bar_compute();
+      }
+      if (!a.forward_only)
+        for (int idx = tid; idx < R * co; idx += kComputeThreads) a.out[(size_t)g0 * NP * co + idx] = xt[(idx / co) * XS + idx % co];
+      bar_compute();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem_base, TMEM_COLS); }
+}
+
+// fp32 [K][N] panels of the fp32 blob -> a (hi, lo) pair of fp16 weight blocks in the canonical K-major no-swizzle UMMA
+// layout.  block element (n, k): n in [0,96) output feature, k in [0,112): k < 96 weight W[k0+k][n0+n] (hi = fp16(W),
+// lo = fp16(W - hi)); k = 96/97 of the hi block: bias hi/lo.
+__global__ void tcx_pack_block_kernel(uint8_t* __restrict__ dst, const float* __restrict__ W, int ldw, int k0, int n0,
+                                      const float* __restrict__ bias) {
+  for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < 96 * WK; idx += gridDim.x * blockDim.x) {
+    const int n = idx / WK, k = idx - n * WK;
+    float hi = 0.f, lo = 0.f;
+    if (k < 96) {
+      const float v = W[(size_t)(k0 + k) * ldw + n0 + n];
+      hi = __half2float(__float2half_rn(v));
+      lo = v - hi;
+    } else if (bias != nullptr && k == 96) {
+      hi = __half2float(__float2half_rn(bias[n0 + n]));
+    } else if (bias != nullptr && k == 97) {
+      const float b = bias[n0 + n];
+      hi = b - __half2float(__float2half_rn(b));
+    }
+    const size_t off = (size_t)(k >> 3) * W_LBO + (size_t)(n >> 3) * W_SBO + (n & 7) * 16 + (k & 7) * 2;
+    *reinterpret_cast<__half*>(dst + off) = __float2half_rn(hi);
+    *reinterpret_cast<__half*>(dst + WBLK_BYTES + off) = __float2half_rn(lo);
+  }
+}
+
+}  // namespace
+
+struct TcxPack {
+  uint8_t* blocks = nullptr;   // [n_layer][14][2][WBLK_BYTES]
+  size_t bytes = 0;
+  bool valid = false;          // packed from the current fp32 blob (packing is lazy: first use after dp_pack)
+};
+
+bool tcx_supported(const Dims& d) {
+  return d.hid == 96 && d.n_head == 4 && d.n_pts == 17 && d.c_in >= 1 && d.c_in <= 5 && d.c_out >= 1 && d.c_out <= 5;
+}
+
+void tcx_free(dp_model* m) {
+  if (m->tcx) {
+    if (m->tcx->blocks) cudaFree(m->tcx->blocks);
+    delete m->tcx;
+    m->tcx = nullptr;
+  }
+}
+
+void tcx_invalidate(dp_model* m) {
+  if (m->tcx) m->tcx->valid = false;
+}
+
+static int pack_block(uint8_t* dst, const float* W, int ldw, int k0, int n0, const float* bias, cudaStream_t s) {
+  tcx_pack_block_kernel<<<12, 256, 0, s>>>(dst, W, ldw, k0, n0, bias);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  return DP_OK;
+}
+
+// Lazy: the split weights (3 MB) are built the first time this engine runs after a dp_pack, not on every weight load.
+static int tcx_ensure_packed(dp_model* m, cudaStream_t s) {
+  const Dims& d = m->d;
+  if (!m->tcx) m->tcx = new TcxPack();
+  if (m->tcx->valid) return DP_OK;
+  const size_t need = (size_t)d.n_layer * BLOCKS_PER_LAYER * 2 * WBLK_BYTES;
+  if (m->tcx->bytes < need) {
+    if (m->tcx->blocks) cudaFree(m->tcx->blocks);
+    m->tcx->blocks = nullptr; m->tcx->bytes = 0;
+    DP_CUDA(cudaMalloc(reinterpret_cast<void**>(&m->tcx->blocks), need));
+    m->tcx->bytes = need;
+  }
+  for (int l = 0; l < d.n_layer; ++l) {
+    const LayerW& L = m->hw.layer[l];
+    uint8_t* b = m->tcx->blocks + (size_t)l * BLOCKS_PER_LAYER * 2 * WBLK_BYTES;
+    int i = 0;
+    // consumption order of the kernel: q, k, v, o, fc1 (two output halves), fc2 (two input halves), cheb1 x3, cheb2 x3
+    for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * 2 * WBLK_BYTES, L.wqkv, 3 * H, 0, part * H, L.bqkv, s));
+    DP_TRY(pack_block(b + (size_t)(i++) * 2 * WBLK_BYTES, L.wo, H, 0, 0, L.bo, s));
+    for (int part = 0; part < 2; ++part) DP_TRY(pack_block(b + (size_t)(i++) * 2 * WBLK_BYTES, L.w1, 2 * H, 0, part * H, L.b1, s));
+    for (int part = 0; part < 2; ++part) DP_TRY(pack_block(b + (size_t)(i++) * 2 * WBLK_BYTES, L.w2, H, part * H, 0, nullptr, s));
+    for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * 2 * WBLK_BYTES, L.wc1, H, part * H, 0, part == 0 ? L.bc1 : nullptr, s));
+    for (int part = 0; part < 3; ++part) DP_TRY(pack_block(b + (size_t)(i++) * 2 * WBLK_BYTES, L.wc2, H, part * H, 0, part == 0 ? L.bc2 : nullptr, s));
+  }
+  m->tcx->valid = true;
+  return DP_OK;
+}
+
+static int tcx_launch(dp_model* m, TcxArgs& a, const StepsArg* inl, cudaStream_t s) {
+  DP_TRY(tcx_ensure_packed(m, s));
+  static bool configured[64] = {};          // function attributes are per device
+  bool& done = configured[m->device & 63];
+  if (!done) {
+    DP_CUDA(cudaFuncSetAttribute(tcx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    done = true;
+  }
+  a.w = m->dw; a.wpack = m->tcx->blocks; a.n_layer = m->d.n_layer; a.c_in = m->d.c_in; a.c_out = m->d.c_out; a.has_temb = m->d.has_temb;
+  a.temb = m->temb;
+  const long n_tiles = (a.n_rows + TP - 1) / TP;
+  const int grid = (int)(n_tiles < m->sm_count ? n_tiles : m->sm_count);
+  tcx_kernel<<<grid, kThreads, SMEM_BYTES, s>>>(a, *inl);
+  count_launch();
+  DP_CUDA(cudaGetLastError());
+  m->last_launch[0] = grid; m->last_launch[1] = kThreads; m->last_launch[2] = SMEM_BYTES;
+  m->last_launch[3] = TP; m->last_launch[4] = DP_ENGINE_TCX; m->last_launch[5] = n_tiles;
+  return DP_OK;
+}
+
+int tcx_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+               const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
+               const unsigned char* mask, cudaStream_t s) {
+  TcxArgs a{};
+  a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
+  a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_steps = n_steps; a.noise = noise; a.mask = mask;
+  a.steps_dev = steps_dev; a.forward_only = 0;
+  return tcx_launch(m, a, inl, s);
+}
+
+// GCNdiff.forward / GCNpose.forward (models/gcndiff.py:101-113, models/gcnpose.py:101-113): one pass, per-sample timesteps.
+// emit_uvxyz (GCNpose only): out is [n,17,c_in+c_out] = [uv | xyz - xyz_root] (runners/diffpose_frame.py:337-343).
+int tcx_forward(dp_model* m, const float* x, const float* t, const unsigned char* mask, float* out, long n, int emit_uvxyz, cudaStream_t s) {
+  const Dims& d = m->d;
+  const long chunk = 1L << 16;  // bounds the per-sample embedding table (chunk * n_layer * hid floats)
+  const int wd = emit_uvxyz ? d.c_in + d.c_out : d.c_out;
+  StepsArg none{};
+  for (long o = 0; o < n; o += chunk) {
+    const long nn = (n - o < chunk) ? (n - o) : chunk;
+    if (d.has_temb) DP_TRY(simt_temb(m, t + o, 1, nullptr, nn, s));
+    TcxArgs a{};
+    a.x_in = x + (size_t)o * d.n_pts * d.c_in; a.x_is_repeated = 1; a.out = out + (size_t)o * d.n_pts * wd;
+    a.n_rows = nn; a.n_pose = nn; a.n_steps = 1; a.noise = nullptr; a.mask = mask; a.steps_dev = nullptr; a.forward_only = 1;
+    a.emit_uvxyz = emit_uvxyz;
+    DP_TRY(tcx_launch(m, a, &none, s));
+  }
+  return DP_OK;
+}
+
+}  // namespace dp

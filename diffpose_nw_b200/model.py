@@ -152,6 +152,8 @@ class _FusedBase(nn.Module):
         self._handle = None
         self._packed_version = None
         self._param_list = None
+        self._packed_sum = None
+        self._calls = 0
         self._engine = _lib.ENGINE_AUTO
 
     def _out_dim(self):
@@ -199,26 +201,39 @@ class _FusedBase(nn.Module):
         return epoch, step
 
     def set_engine(self, engine):
-        """'auto' | 'fp32' | 'tc' | 'tcg' -- which kernel family runs the denoiser (see include/diffpose_b200.h)."""
-        self._engine = {"auto": _lib.ENGINE_AUTO, "fp32": _lib.ENGINE_FP32, "tc": _lib.ENGINE_TC, "tcg": _lib.ENGINE_TCG}[engine]
+        """'auto' | 'fp32' | 'tcx' | 'tcg' -- which kernel family runs the model (see include/diffpose_b200.h).
+        'auto': the sampler runs on 'tcg' (fp16-operand tensor cores; its rounding is damped by the DDIM schedule) and
+        plain forward calls -- GCNdiff.forward, the GCNpose lifter -- on 'tcx' (split-precision tensor cores, fp32-level)."""
+        self._engine = {"auto": _lib.ENGINE_AUTO, "fp32": _lib.ENGINE_FP32, "tcx": _lib.ENGINE_TCX, "tcg": _lib.ENGINE_TCG}[engine]
         if self._handle is not None:
             _lib.check(_lib.load().dp_set_engine(self._handle, self._engine), "dp_set_engine")
         return self
 
     def engine(self):
+        """Engine the SAMPLER (dp_sample) uses with the current setting."""
         self._ensure_packed(self._device())
-        return {1: "fp32", 2: "tc", 3: "tcg"}[_lib.load().dp_get_engine(self._handle)]
+        return _lib.ENGINE_NAMES[_lib.load().dp_get_engine(self._handle)]
+
+    def forward_engine(self):
+        """Engine a forward call (dp_forward / dp_lift) uses with the current setting."""
+        self._ensure_packed(self._device())
+        return _lib.ENGINE_NAMES[_lib.load().dp_get_forward_engine(self._handle)]
 
     # ---------------------------------------------------------------- device state
     def _device(self):
         return self.gconv_input.weight.device
 
-    def _weights_version(self):
-        """Fingerprint that changes whenever the parameters do.  In training mode every parameter is checked (an
-        optimiser step bumps each `_version`); in eval() mode -- the sampling path, where this runs once per batch and a
-        123-tensor walk would cost more host time than the kernel takes -- only the first and last parameter are looked
-        at.  `load_state_dict`, `.to()/.cuda()` and `repack()` invalidate the packed copy explicitly."""
-        if self.training:
+    def _weights_version(self, full):
+        """Fingerprint of (storage, version counter) of the parameters.  In training mode every parameter is checked on
+        every call (an optimiser step bumps each `_version`).  In eval() mode -- the sampling path, where this runs once
+        per batch and a 123-tensor walk would cost more host time than the kernel takes -- the first and last parameter
+        are checked on every call and ALL of them on every 64th.  `load_state_dict`, `.to()/.cuda()`, `train()` and
+        `repack()` invalidate the packed copy explicitly.
+
+        What NO version counter sees: writes through `param.data` -- `p.data.copy_(...)`, which is exactly what the
+        reference's `EMAHelper.ema()` does (models/ema.py:27-29).  After such a write call `repack()` (the `EMAHelper`
+        of this package does it for you); `check_weights()` verifies the device copy against the live parameters."""
+        if full:
             return tuple((p.data_ptr(), p._version) for p in self.parameters())
         ps = self._param_list
         if ps is None:
@@ -227,16 +242,69 @@ class _FusedBase(nn.Module):
         return (len(ps), a.data_ptr(), a._version, b.data_ptr(), b._version)
 
     def repack(self):
-        """Force the device-side packed weights to be rebuilt on the next call (after in-place edits in eval mode)."""
+        """Force the device-side packed weights to be rebuilt on the next call.  REQUIRED after writes that bypass autograd's
+        version counters (`param.data.copy_()`, `EMAHelper.ema()` of the reference) and after in-place edits in eval mode."""
         self._packed_version = None
         self._param_list = None
         return self
 
-    def _apply(self, fn, *args, **kwargs):
-        out = super()._apply(fn, *args, **kwargs)
+    def check_weights(self, repack=True):
+        """Debugging aid: compare a checksum of the LIVE parameters with the one taken when the device copy was packed
+        (one small reduction + a device->host read, i.e. a synchronisation -- not for the per-batch path).  Returns True
+        when the packed copy is current; otherwise repacks (unless `repack=False`) and returns False."""
+        if self._packed_sum is None or self._packed_version is None:
+            return False
+        live = self._checksum(self._flat_params(self._device()))
+        ok = bool(torch.equal(live, self._packed_sum))
+        if not ok and repack:
+            self.repack()
+        return ok
+
+    def _flat_params(self, device):
+        sd = dict(self.named_parameters())
+        return torch.cat([sd[k].detach().reshape(-1).to(device=device, dtype=torch.float32)
+                          for k in _param_order(self.n_layers, self._has_temb)]).contiguous()
+
+    @staticmethod
+    def _checksum(flat):
+        # two position-weighted fp64 sums: a changed, moved or swapped value changes at least one of them
+        w = torch.arange(1, flat.numel() + 1, device=flat.device, dtype=torch.float64)
+        f = flat.double()
+        return torch.stack([f.sum(), (f * w).sum()])
+
+    def _drop_handle(self):
+        if getattr(self, "_handle", None) is not None and _lib._lib is not None:
+            _lib._lib.dp_destroy(self._handle)
+        self._handle = None
         self._packed_version = None
         self._param_list = None
+        self._packed_sum = None
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        # .to()/.cuda() may have moved the parameters to another device: the handle (weights blob, scratch, SM count) belongs
+        # to the device it was created on, so it is re-created on the next call
+        self._drop_handle()
+        if hasattr(self, "_mask_cache"):
+            object.__delattr__(self, "_mask_cache")
         return out
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_handle"] = None              # a ctypes pointer is neither picklable nor shareable between copies
+        state["_packed_version"] = None
+        state["_param_list"] = None
+        state["_packed_sum"] = None
+        state.pop("_mask_cache", None)
+        return state
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__getstate__().items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        return new
 
     def train(self, mode=True):
         out = super().train(mode)
@@ -247,25 +315,29 @@ class _FusedBase(nn.Module):
         if device.type != "cuda":
             raise RuntimeError("diffpose_nw_b200 runs on CUDA only (no CPU fallback): move the model and its inputs to a GPU")
         lib = _lib.load()
+        if self._handle is not None and device != self._handle_dev:     # inputs on another GPU than the handle's: re-create it there
+            self._drop_handle()
         if self._handle is None:
             h = ctypes.c_void_p()
             with torch.cuda.device(device):
                 _lib.check(lib.dp_create(ctypes.byref(h), self.n_pts, self._c_in, self._c_out, self.hid_dim,
                                          self.n_layers, self.n_head, 1 if self._has_temb else 0), "dp_create")
             self._handle = h
+            self._handle_dev = device
             _lib.check(lib.dp_set_engine(h, self._engine), "dp_set_engine")
-        version = self._weights_version()
-        if version != self._packed_version:
-            sd = dict(self.named_parameters())
-            flat = torch.cat([sd[k].detach().reshape(-1).to(device=device, dtype=torch.float32)
-                              for k in _param_order(self.n_layers, self._has_temb)]).contiguous()
+        self._calls += 1
+        full = self.training or (self._calls & 63) == 0
+        version = self._weights_version(full)
+        if self._packed_version is None or version != self._packed_version[1 if full else 0]:
+            flat = self._flat_params(device)
             adj = torch.as_tensor(self.adj, dtype=torch.float32).detach().cpu().contiguous()
             if tuple(adj.shape) != (self.n_pts, self.n_pts):
                 raise RuntimeError(f"adj must be [{self.n_pts},{self.n_pts}], got {tuple(adj.shape)}")
             with torch.cuda.device(device):
                 stream = torch.cuda.current_stream(device).cuda_stream
                 _lib.check(lib.dp_pack(self._handle, flat.data_ptr(), flat.numel(), adj.data_ptr(), stream), "dp_pack")
-            self._packed_version = version
+            self._packed_sum = self._checksum(flat)
+            self._packed_version = (self._weights_version(False), self._weights_version(True))
 
     def _mask_bytes(self, mask, device):
         if mask is None:
@@ -322,9 +394,7 @@ class _FusedBase(nn.Module):
 
     def __del__(self):
         try:
-            if getattr(self, "_handle", None) is not None and _lib._lib is not None:
-                _lib._lib.dp_destroy(self._handle)
-                self._handle = None
+            self._drop_handle()
         except Exception:
             pass
 
@@ -348,3 +418,65 @@ class FusedGCNpose(_FusedBase):
 
     def forward(self, x, mask):
         return self._forward(x, mask, None)
+
+    def lift(self, input_2d, mask=None):
+        """The runner's glue between the two stages in ONE launch (`dp_lift`): `xyz = model_pose(input_2d, mask)`,
+        root-centre (out of place), `cat([input_2d, xyz], 2)` (runners/diffpose_frame.py:337-343) -> [n,17,5]."""
+        x = self._check_x(input_2d, self._c_in)
+        dev = x.device
+        self._ensure_packed(dev)
+        n = x.shape[0]
+        out = torch.empty(n, self.n_pts, self._c_in + self._c_out, device=dev, dtype=torch.float32)
+        if n == 0:
+            return out
+        mb = self._mask_bytes(mask, dev)
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(_lib.load().dp_lift(self._handle, x.data_ptr(), mb.data_ptr() if mb is not None else None, out.data_ptr(), n, stream),
+                       "dp_lift")
+        return out
+
+
+class EMAHelper(object):
+    """Drop-in for the reference's `models/ema.py::EMAHelper` (same methods, same arithmetic) that keeps the fused
+    modules coherent: `ema()` writes the shadow into the parameters through `param.data.copy_` exactly like the reference
+    (models/ema.py:27-29) -- a write no autograd version counter sees -- and then calls `repack()` on the module, so the
+    device-side packed weights can never be stale after it."""
+
+    def __init__(self, mu=0.999):
+        self.mu = mu
+        self.shadow = {}
+
+    @staticmethod
+    def _inner(module):
+        return module.module if isinstance(module, nn.DataParallel) else module
+
+    def register(self, module):
+        for name, param in self._inner(module).named_parameters():
+            if param.requires_grad:
+                self.shadow[name] = param.data.clone()
+
+    def update(self, module):
+        for name, param in self._inner(module).named_parameters():
+            if param.requires_grad:
+                self.shadow[name].data = (1. - self.mu) * param.data + self.mu * self.shadow[name].data
+
+    def ema(self, module):
+        inner = self._inner(module)
+        for name, param in inner.named_parameters():
+            if param.requires_grad:
+                param.data.copy_(self.shadow[name].data)
+        if hasattr(inner, "repack"):
+            inner.repack()
+
+    def ema_copy(self, module):
+        import copy
+        module_copy = copy.deepcopy(self._inner(module))     # (the reference rebuilds from config; a deep copy is equivalent)
+        self.ema(module_copy)
+        return nn.DataParallel(module_copy) if isinstance(module, nn.DataParallel) else module_copy
+
+    def state_dict(self):
+        return self.shadow
+
+    def load_state_dict(self, state_dict):
+        self.shadow = state_dict

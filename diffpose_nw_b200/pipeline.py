@@ -27,9 +27,9 @@ def lift_and_refine(model_diff, x_uvxyz=None, *, model_pose=None, input_2d=None,
     """Two-stage inference for one batch.  Give either `x_uvxyz` [B,17,5] or (`model_pose`, `input_2d` [B,17,2]).
     Returns the hypothesis-averaged uvxyz [B,17,5]."""
     if x_uvxyz is None:
-        xyz = model_pose(input_2d, src_mask)
-        xyz = xyz - xyz[:, :1, :]                       # out-of-place root-centring (SURVEY.md 8a quirk 4)
-        x_uvxyz = torch.cat([input_2d.to(xyz.dtype), xyz], dim=2)
+        # lift + out-of-place root-centring (SURVEY.md 8a quirk 4) + concat in ONE launch (dp_lift); the sampler below is
+        # the second and last launch of the batch (kernel-side repeat, hypothesis mean fused into its final store)
+        x_uvxyz = getattr(model_pose, "module", model_pose).lift(input_2d, src_mask)
     return sample(model_diff, x_uvxyz, src_mask, seq, betas, eta=eta, noise=noise, n_hyp=test_times,
                   repeat_input=True, mean_over_hyp=True)
 

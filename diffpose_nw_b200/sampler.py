@@ -77,6 +77,8 @@ def ddim_steps(b, seq, eta=0.0):
     return steps
 
 
+NOISE_CHUNK_BYTES = 2 << 30    # device-drawn noise held at any one time by `sample` (eta > 0, no caller noise)
+
 _STEP_CACHE = {}      # (betas identity, seq, eta) -> (DpStep array, betas kept alive); a handful of schedules per process
 
 
@@ -128,33 +130,62 @@ def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_inpu
         steps = cached_ddim_steps(b, seq, eta)
     T = len(steps)
     total = n_pose * n_hyp
+    c = m._c_in
     nz = None
+    draw = False
     if noise is not None:
         nz = torch.as_tensor(noise, device=dev).detach().to(torch.float32).contiguous()
-        if tuple(nz.shape) != (T, total, m.n_pts, m._c_in):
-            raise RuntimeError(f"noise must be [{T},{total},{m.n_pts},{m._c_in}], got {tuple(nz.shape)}")
+        if tuple(nz.shape) != (T, total, m.n_pts, c):
+            raise RuntimeError(f"noise must be [{T},{total},{m.n_pts},{c}], got {tuple(nz.shape)}")
     elif any(s.c1 != 0.0 for s in steps):
-        # eta > 0 without caller noise: draw it where the reference does (one randn_like per step)
-        nz = torch.randn(T, total, m.n_pts, m._c_in, device=dev, dtype=torch.float32)
+        draw = True        # eta > 0 without caller noise: N(0,1) draws in place of the reference's per-step randn_like (:65)
     out_rows = n_pose if mean_over_hyp else total
-    out = torch.empty(out_rows, m.n_pts, m._c_in, device=dev, dtype=torch.float32)
+    out = torch.empty(out_rows, m.n_pts, c, device=dev, dtype=torch.float32)
     if total == 0:
         return out
     mb = m._mask_bytes(src_mask, dev)
+    lib = _lib.load()
+    mask_ptr = mb.data_ptr() if mb is not None else None
 
-    def launch():
+    def launch(x_t, out_t, n_p, nz_t, repeated):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = _lib.load().dp_sample(m._handle, xc.data_ptr(), 0 if repeat_input else 1, out.data_ptr(), n_pose,
-                                   n_hyp, steps, T, nz.data_ptr() if nz is not None else None,
-                                   mb.data_ptr() if mb is not None else None, 1 if mean_over_hyp else 0, stream)
+        rc = lib.dp_sample(m._handle, x_t.data_ptr(), 1 if repeated else 0, out_t.data_ptr(), n_p, n_hyp, steps, T,
+                           nz_t.data_ptr() if nz_t is not None else None, mask_ptr, 1 if mean_over_hyp else 0, stream)
         if rc != 0:
             _lib.check(rc, "dp_sample")
 
+    def run():
+        if not draw:
+            return launch(xc, out, n_pose, nz, not repeat_input)
+        # Device-drawn noise is needed as [T, rows, 17, c] by the kernel (it runs all T steps of a tile in one go).  The
+        # reference holds one step's draw at a time; to keep memory bounded like that, a large call is cut into pose chunks
+        # whose noise fits NOISE_CHUNK_BYTES (the chunks are independent: poses are).  The random STREAM differs from the
+        # reference's (same distribution, different draws for a given seed) -- pass `noise=` for comparable results.
+        row_bytes = m.n_pts * c * 4
+        per_chunk = max(1, NOISE_CHUNK_BYTES // (T * row_bytes * n_hyp))
+        if per_chunk >= n_pose:
+            return launch(xc, out, n_pose, torch.randn(T, total, m.n_pts, c, device=dev, dtype=torch.float32), not repeat_input)
+        xv = xc if repeat_input else xc.view(n_hyp, n_pose, m.n_pts, c)
+        ov = out if mean_over_hyp else out.view(n_hyp, n_pose, m.n_pts, c)
+        buf = torch.empty(T, per_chunk * n_hyp, m.n_pts, c, device=dev, dtype=torch.float32)
+        for lo in range(0, n_pose, per_chunk):
+            hi = min(n_pose, lo + per_chunk)
+            k = hi - lo
+            nzc = buf[:, : k * n_hyp] if k == per_chunk else torch.empty(T, k * n_hyp, m.n_pts, c, device=dev, dtype=torch.float32)
+            nzc.normal_()
+            x_c = xv[lo:hi] if repeat_input else xv[:, lo:hi].reshape(k * n_hyp, m.n_pts, c).contiguous()
+            if mean_over_hyp:
+                launch(x_c, ov[lo:hi], k, nzc, not repeat_input)
+            else:
+                o_c = torch.empty(k * n_hyp, m.n_pts, c, device=dev, dtype=torch.float32)
+                launch(x_c, o_c, k, nzc, not repeat_input)
+                ov[:, lo:hi] = o_c.view(n_hyp, k, m.n_pts, c)
+
     if torch.cuda.current_device() == dev.index:      # the usual case: no device switch on the per-batch path
-        launch()
+        run()
     else:
         with torch.cuda.device(dev):
-            launch()
+            run()
     return out
 
 

@@ -13,9 +13,14 @@
  *   - all tensor pointers are DEVICE pointers to contiguous fp32 unless the name ends in _host.
  *   - the library borrows caller memory for the duration of a call; it owns only its packed weights and
  *     scratch, released by dp_destroy().
- *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  Calls only enqueue work;
- *     they never synchronise the device.
- *   - one host thread per handle; one process per GPU.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).  dp_forward, dp_lift, dp_sample and
+ *     dp_metrics only enqueue work on it.  Exceptions, all off the per-batch path: dp_pack synchronises the stream once
+ *     (it stages host-side graph matrices); dp_sample synchronises once when a schedule of MORE than 64 steps changes
+ *     (the new step table is uploaded from the handle's own copy); scratch buffers (time-embedding table, hypothesis
+ *     scratch of the non-default engines) grow with cudaMalloc the first time a larger batch or schedule is seen.
+ *     A call that neither grows a buffer nor changes a long schedule is CUDA-graph capturable.
+ *   - a handle belongs to the device that was current at dp_create; calls made with another device current return
+ *     DP_ERR_STATE.  One host thread per handle; one process per GPU.
  */
 #ifndef DIFFPOSE_B200_H
 #define DIFFPOSE_B200_H
@@ -34,16 +39,19 @@ enum dp_status {
   DP_ERR_UNSUPPORTED = -4  /* the requested engine cannot run this configuration */
 };
 
-/* Which kernel family executes the denoiser. */
+/* Which kernel family executes the denoiser / lifter. */
 enum dp_engine {
-  DP_ENGINE_AUTO = 0,  /* DP_ENGINE_TCG when the configuration allows it, else fp32                 */
-  DP_ENGINE_FP32 = 1,  /* fp32 FMA persistent kernel: every contraction in fp32 (bit-level reference) */
-  DP_ENGINE_TC = 2,    /* first tcgen05 persistent kernel, kept for A/B measurements: fp16 operands (11-bit
-                          significand, same as TF32), fp32 accumulation in TMEM, graph operators and attention
-                          on the CUDA cores; hid_dim=96, n_head=4, n_pts=17 only                        */
-  DP_ENGINE_TCG = 3    /* second-generation tcgen05 kernel (the default): every contraction on the tensor cores
-                          (projections, 17x17 graph operators, attention, in/out convolutions), residual stream
-                          in TMEM, dedicated MMA-issuer warp; same limits                                */
+  DP_ENGINE_AUTO = 0,  /* dp_sample: DP_ENGINE_TCG; dp_forward / dp_lift: DP_ENGINE_TCX (a forward output is not damped
+                          by a DDIM schedule, so it takes the accurate path); fp32 when the configuration is outside
+                          the tensor-core engines' limits (hid_dim=96, n_head=4, n_pts=17, coords_dim <= 5)          */
+  DP_ENGINE_FP32 = 1,  /* fp32 FMA persistent kernel: every contraction in fp32 (bit-level reference)                */
+  DP_ENGINE_TCX = 2,   /* split-precision tcgen05 kernel: dense projections as three fp16 products per K step
+                          (A_hi W_hi + A_lo W_hi + A_hi W_lo, fp32 accumulation in TMEM), everything else fp32 on the
+                          CUDA cores: <= 2e-5 from the fp32 reference                                                */
+  DP_ENGINE_TCG = 3    /* the fast tcgen05 kernel (sampler default): every contraction on the tensor cores with fp16
+                          operands (11-bit significand, as TF32) -- projections, 17x17 graph operators, attention,
+                          in/out convolutions -- residual stream in TMEM, dedicated MMA-issuer warp.  fp16 operand
+                          range: activations beyond +-65504 SATURATE (they never become inf/NaN)                     */
 };
 
 /* One DDIM step.  The scalars are evaluated by the caller with the reference's own fp32 tensor ops
@@ -88,8 +96,11 @@ int dp_pack(dp_handle h, const float* params, long n_floats, const float* adj_ho
 
 /* Select the engine for subsequent dp_forward/dp_sample calls (default DP_ENGINE_AUTO). */
 int dp_set_engine(dp_handle h, int engine);
-/* Engine that a call with the current setting would use (DP_ENGINE_FP32, DP_ENGINE_TC or DP_ENGINE_TCG). */
+/* Engine that dp_sample / dp_forward (and dp_lift) would use with the current setting: DP_ENGINE_FP32, _TCX or _TCG. */
 int dp_get_engine(dp_handle h);
+int dp_get_forward_engine(dp_handle h);
+/* CUDA device ordinal the handle was created on. */
+int dp_device(dp_handle h);
 
 /* Replaces GCNdiff.forward(x, mask, t, cemd) (models/gcndiff.py:101-113; call sites
  * common/utils_diff.py:58, runners/diffpose_frame.py:225) and GCNpose.forward(x, mask)
@@ -99,13 +110,22 @@ int dp_get_engine(dp_handle h);
  *   out [n,n_pts,c_out]. */
 int dp_forward(dp_handle h, const float* x, const float* t, const unsigned char* mask, float* out, long n, void* stream);
 
+/* Replaces the glue between the two stages of the evaluation loop (runners/diffpose_frame.py:337-343):
+ *     output_xyz = model_pose(input_2d, src_mask); output_xyz[:, :, :] -= output_xyz[:, :1, :];
+ *     output_uvxyz = torch.cat([input_2d, output_xyz], dim=2)
+ * in ONE launch on a GCNpose handle (has_temb = 0): uv [n,n_pts,c_in] -> out_uvxyz [n,n_pts,c_in+c_out] =
+ * [uv | xyz - xyz[root]].  The root-centring is done OUT OF PLACE (the intended semantics; the reference's aliased
+ * in-place form leaves joints 1..16 unchanged on CPU and races on CUDA). */
+int dp_lift(dp_handle h, const float* uv, const unsigned char* mask, float* out_uvxyz, long n, void* stream);
+
 /* Replaces generalized_steps(x, src_mask, seq, model, b, eta=...) (common/utils_diff.py:46-67) plus the
  * hypothesis handling around it (runners/diffpose_frame.py:342 `.repeat(test_times,1,1)` and :382
  * `mean(reshape(test_times,-1,17,5),0)`), in ONE persistent launch for all T steps.
  *   x_in      [n_rows_in,n_pts,c] with n_rows_in = n_pose*n_hyp if x_is_repeated else n_pose
  *             (the library reads pose b for every hypothesis h when x_is_repeated = 0);
  *   x_out     [n_pose*n_hyp,n_pts,c] hypothesis-major (index h*n_pose+b) when mean_over_hyp = 0,
- *             [n_pose,n_pts,c] when mean_over_hyp = 1;
+ *             [n_pose,n_pts,c] when mean_over_hyp = 1 (DP_ENGINE_TCG folds the mean into the kernel's final store:
+ *             one launch, no [n_pose*n_hyp] intermediate);
  *   steps_host T entries in execution order (largest t first);
  *   noise     [T,n_pose*n_hyp,n_pts,c] host-drawn N(0,1) replacing randn_like (:65), or NULL (term skipped;
  *             exact when every c1 = 0, i.e. eta = 0);
@@ -122,36 +142,6 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
  *   per_pose: optional [n,2] fp32 device output (mpjpe, p_mpjpe per pose) or NULL. */
 int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                double* sums, float* per_pose, void* stream);
-
-/* Diagnostic "UMMA lab": copies `smem_image` (device pointer, image_bytes % 16 == 0) to shared memory offset 0, issues the
- * listed tcgen05.mma.kind::f16 instructions in order (descriptor fields in bytes, offsets relative to the image start;
- * SWIZZLE_NONE canonical layouts; idesc = the 32-bit instruction descriptor), then writes TMEM lanes 0..127, columns
- * 0..ncols-1 to tmem_out[128][ncols] (device, fp32).  Synchronises the stream.  The GPU tests use it to pin every operand
- * flavour the tensor-core engine relies on against numpy. */
-typedef struct dp_mma_op {
-  unsigned a_off, a_lbo, a_sbo;   /* A operand: start, leading-dimension byte offset, stride-dimension byte offset */
-  unsigned b_off, b_lbo, b_sbo;   /* B operand */
-  unsigned idesc;                 /* instruction descriptor (formats, majors, N>>3 at bit 17, M>>4 at bit 24)    */
-  unsigned tmem_col;              /* first accumulator column                                                     */
-  unsigned accumulate;            /* bit 0: 0 D = A*B, 1 D += A*B; bit 1 (dp_selftest_umma_ts): A is in TMEM at column a_off */
-} dp_mma_op;
-int dp_selftest_umma(const void* smem_image, int image_bytes, const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols,
-                     void* stream);
-/* Same, after preloading tensor memory: tmem_image is a device array [128 lanes][tmem_ncols] of 32-bit words written to
- * columns tmem_col0.. (tmem_ncols % 8 == 0); ops with accumulate bit 1 read their A operand from TMEM (two fp16 per word). */
-int dp_selftest_umma_ts(const void* smem_image, int image_bytes, const void* tmem_image, int tmem_col0, int tmem_ncols,
-                        const dp_mma_op* ops_host, int n_ops, float* tmem_out, int ncols, void* stream);
-
-/* SM cycles of the last dp_selftest_umma[_ts] launch: out2[0] = to issue all MMAs and the commit (one thread),
- * out2[1] = from the first issue until the committed mbarrier was observed (host array of 2). */
-int dp_selftest_cycles(long long* out2);
-
-/* Diagnostic: while dev_buf is set (device pointer, `capacity` 64-bit slots; NULL/0 switches it off), thread 0 of CTA 0 of
- * the DP_ENGINE_TCG kernel stores (clock64() << 1) | kind at every hand-over between the compute warps and the MMA issuer
- * (kind 0: "operands ready" is about to be signalled, kind 1: "accumulator ready" was observed) in program order in the
- * first half of the buffer; the issuer stores clock64() before/after each of its waits in the second half.  Used by
- * tools/phase_trace.py to attribute the per-layer time to the individual epilogues and MMA groups. */
-int dp_set_trace(dp_handle h, long long* dev_buf, int capacity);
 
 /* Number of kernels this library has launched in this process (bench.py reports it as gpu_launches). */
 long dp_launch_count(void);

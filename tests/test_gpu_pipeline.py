@@ -26,15 +26,16 @@ def _models():
     return adj, diff, sd_d, pose, sd_p
 
 
-@pytest.mark.parametrize("engine", ["fp32", "auto", "mixed"])
+@pytest.mark.parametrize("engine", ["fp32", "auto", "tcg"])
 def test_two_stage_pipeline_vs_oracle(engine):
-    """mixed = fp32 lifter + tensor-core denoiser.  The denoiser's fp16-operand error reaches x damped by the DDIM
-    coefficients (a few 1e-5 here); the lifter's output IS the xyz input, undamped, so with these random weights
-    (|xyz| up to 2) a tensor-core lifter alone costs up to ~2e-3 (oracle/tc_emulation.py predicts the same figure)."""
+    """auto (the default) = split-precision tensor-core lifter (tcx) + fp16-operand tensor-core sampler (tcg): within the
+    north_star tolerance (1e-3 abs, 0.05 mm).  The sampler's fp16-operand error reaches x damped by the DDIM coefficients
+    (a few 1e-5 here); the lifter's output IS the xyz input, undamped, which is why it runs on tcx.  "tcg" forces the
+    fp16-operand engine for the lifter too: up to ~2e-3 with these random weights (|xyz| up to 2.6), reported, not default."""
     dev = torch.device("cuda:0")
     adj, diff, sd_d, pose, sd_p = _models()
-    diff = diff.to(dev).set_engine("auto" if engine == "mixed" else engine)
-    pose = pose.to(dev).set_engine("fp32" if engine == "mixed" else engine)
+    diff = diff.to(dev).set_engine(engine)
+    pose = pose.to(dev).set_engine(engine)
     B, Hh, seq, eta = 23, 5, [0, 6], 1.0
     uv = O.synthetic_poses(B, seed=30)[:, :, :2].contiguous()
     tgt = O.synthetic_targets(O.synthetic_poses(B, seed=30), seed=31)
@@ -49,10 +50,20 @@ def test_two_stage_pipeline_vs_oracle(engine):
     ref_xyz = O.root_centre(ref[:, :, 2:])
     want = (O.mpjpe(ref_xyz, O.root_centre(tgt)).item() * 1000, float(O.p_mpjpe_per_pose(ref_xyz.numpy(), O.root_centre(tgt).numpy()).mean()) * 1000)
     # product
+    l0 = D._lib.launch_count()
     out = D.lift_and_refine(diff, model_pose=pose, input_2d=uv.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(),
                             eta=eta, test_times=Hh, noise=noise.to(dev))
-    tol = {"fp32": 2e-5, "mixed": 1e-3, "auto": 3e-3}[engine]
-    assert (out.cpu() - ref).abs().max().item() < tol
+    n_launch = D._lib.launch_count() - l0
+    tol = {"fp32": 2e-5, "auto": 1e-3, "tcg": 3e-3}[engine]
+    err = (out.cpu() - ref).abs().max().item()
+    print(f"two-stage / {engine}: max|dx|={err:.2e} launches (incl. one-time packing)={n_launch}")
+    assert err < tol
+    if engine == "auto":
+        # second batch: everything is packed and cached -> exactly two launches (dp_lift, dp_sample)
+        l0 = D._lib.launch_count()
+        D.lift_and_refine(diff, model_pose=pose, input_2d=uv.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(),
+                          eta=eta, test_times=Hh, noise=noise.to(dev))
+        assert D._lib.launch_count() - l0 == 2
     sums = D.evaluate_shard(diff, None, tgt.to(dev), src_mask=mask.to(dev), seq=seq, betas=betas(), eta=eta, test_times=Hh,
                             noise=noise.to(dev), model_pose=pose, input_2d=uv.to(dev), batch_size=10)
     m, pm, cnt = D.reduce_metrics(sums)
@@ -146,6 +157,6 @@ def test_second_device_in_one_process():
     torch.cuda.set_device(0)
     b = D.generalized_steps(x.to("cuda:1"), None, [0, 12], m1, betas())[0][-1]
     assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())
-    for eng in ("fp32", "tc"):
+    for eng in ("fp32", "tcx"):
         c = D.generalized_steps(x.to("cuda:1"), None, [0, 12], m1.set_engine(eng), betas())[0][-1]
         assert (c.cpu() - a.cpu()).abs().max().item() < 1e-3

@@ -1,6 +1,7 @@
-"""GPU (-m gpu): the tcgen05 engine.  First the isolated 128x96x96 tensor-core product (layouts, descriptors, TMA
-staging, TMEM read-back), then the whole sampler against (a) the CPU emulation of its fp16 rounding points -- tight
-tolerance, catches indexing bugs -- and (b) the fp32 oracle at the north_star tolerance."""
+"""GPU (-m gpu): the two tcgen05 engines.
+  tcg (sampler default, fp16 operands): against (a) the CPU emulation of its fp16 rounding points -- tight tolerance,
+      catches indexing bugs -- and (b) the fp32 oracle at the north_star tolerance (1e-3 abs, 0.05 mm), every case.
+  tcx (forward / lifter default, split-precision operands): against the fp32 oracle at fp32-level tolerance."""
 import numpy as np
 import pytest
 import torch
@@ -19,11 +20,14 @@ def dev():
     return torch.device("cuda:0")
 
 
-EMU = {"tc": E.gcndiff_forward_tc, "tcg": lambda *a: E.gcndiff_forward_tcg(*a, p16=True, temb_in_gc2=True)}   # the sampler's form
-ENGINE_ID = {"tc": 2, "tcg": 3}
+# tcg: the sampler's form of the rounding-point emulation; tcx has no rounding points above fp32 level: its emulation IS the oracle
+EMU = {"tcx": lambda sd, adj, nl, nh, a, m, tt: O.gcndiff_forward(sd, adj, nl, nh, a, m, tt),
+       "tcg": lambda *a: E.gcndiff_forward_tcg(*a, p16=True, temb_in_gc2=True)}
+ENGINE_ID = {"tcx": 2, "tcg": 3}
+TCX_TOL = 5e-5      # split-precision engine vs the fp32 oracle (|x| ~ 1; accumulation-order level)
 
 
-@pytest.mark.parametrize("engine", ["tc", "tcg"])
+@pytest.mark.parametrize("engine", ["tcx", "tcg"])
 @pytest.mark.parametrize("tag", ["A", "A1", "B", "C", "D"])
 def test_tc_engine_vs_emulation_and_oracle(golden, tag, engine):
     cfg, adj, model, sd = build_diff(tag, golden)
@@ -43,12 +47,12 @@ def test_tc_engine_vs_emulation_and_oracle(golden, tag, engine):
     # vs the emulation: only accumulation order, reciprocal-vs-division and fp16 double rounding differ; those are
     # amplified by the sampler dynamics exactly like the operand rounding itself (amp), an indexing bug is not
     assert e_emu < max(1e-4, 1.0 * amp), f"{tag}: kernel disagrees with its rounding-point emulation ({e_emu:.3e})"
-    # vs the reference: north_star tolerance; case D (50 steps on perturbed, strongly amplifying weights) is reported
-    # against a 1e-2 bound because the fp16/TF32 operand precision itself (amp) exceeds 1e-3 there
-    assert e_ref < (1e-2 if tag == "D" else 1e-3)
+    # vs the reference: the north_star tolerance (1e-3 abs) on every case, the 50-step perturbed-weights case D included;
+    # the split-precision engine at fp32 level (case D: 50 amplifying steps)
+    assert e_ref < (1e-3 if engine == "tcg" else (4 * TCX_TOL if tag == "D" else TCX_TOL))
 
 
-@pytest.mark.parametrize("engine", ["tc", "tcg"])
+@pytest.mark.parametrize("engine", ["tcx", "tcg"])
 def test_tc_default_init_50_steps(engine):
     """BASELINE configs[3] schedule (T = 50, H = 2, eta = 1) on default-init weights: within 1e-3 of the fp32 oracle."""
     cfg = O.default_config()
@@ -68,11 +72,11 @@ def test_tc_default_init_50_steps(engine):
     tgt = O.synthetic_targets(x)
     m_ref = O.mpjpe(O.root_centre(O.hypothesis_mean(ref, Hh)[:, :, 2:]), tgt).item() * 1000
     m_out = O.mpjpe(O.root_centre(O.hypothesis_mean(out, Hh)[:, :, 2:]), tgt).item() * 1000
-    print(f"T=50 default-init: max|dx|={err:.2e} dMPJPE={abs(m_ref - m_out):.4f} mm")
-    assert err < 1e-3 and abs(m_ref - m_out) < 0.05
+    print(f"T=50 default-init / {engine}: max|dx|={err:.2e} dMPJPE={abs(m_ref - m_out):.4f} mm")
+    assert err < (1e-3 if engine == "tcg" else TCX_TOL) and abs(m_ref - m_out) < 0.05
 
 
-@pytest.mark.parametrize("engine", ["tc", "tcg"])
+@pytest.mark.parametrize("engine", ["tcx", "tcg"])
 def test_tc_matches_fp32_engine_on_many_tiles(engine):
     """Multi-tile / ragged last tile / persistent loop: 1500 poses on both engines."""
     cfg = O.default_config()
@@ -107,10 +111,29 @@ def test_tcg_repeatable_across_ring_wraps():
     assert (first - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("tag", ["A", "A1", "B", "C", "D"])
+def test_forward_default_engine_is_split_precision(golden, tag):
+    """GCNdiff.forward (per-sample timesteps, partial key mask in B) with the DEFAULT engine setting: forward calls run on
+    the split-precision tensor-core engine and match the reference's eps at fp32 level."""
+    from _cases import build_diff
+    cfg, adj, model, sd = build_diff(tag, golden)
+    model = model.to(dev())
+    assert model.forward_engine() == "tcx" and model.engine() == "tcg"
+    x, mask, tt = t(golden, f"{tag}.x"), mask_for(tag, golden), t(golden, f"{tag}.t")
+    eps = model(x.to(dev()), mask.to(dev()), tt.to(dev()), 0).cpu()
+    assert model.last_launch()[4] == 2
+    ref = t(golden, f"{tag}.eps")
+    scale = max(1.0, ref.abs().max().item())
+    err = (eps - ref).abs().max().item()
+    print(f"forward {tag} / tcx: |eps - ref|={err:.2e} scale={scale:.2f}")
+    assert err < 2e-5 * scale
+
+
 @pytest.mark.parametrize("tag", ["A", "A1", "B", "C"])
 def test_tcg_forward_per_sample_t(golden, tag):
-    """GCNdiff.forward (per-sample timesteps, partial key mask in B) on the tensor-core engine: close to its rounding-point
-    emulation, and to the fp32 reference within the operand precision."""
+    """GCNdiff.forward (per-sample timesteps, partial key mask in B) on the fp16-operand engine when it is selected
+    explicitly (the default for forward calls is tcx, above): close to its rounding-point emulation; against the fp32
+    reference only within the undamped operand precision (that is why it is not the default for forward calls)."""
     from _cases import build_diff
     cfg, adj, model, sd = build_diff(tag, golden)
     model = model.to(dev()).set_engine("tcg")
@@ -127,15 +150,43 @@ def test_tcg_forward_per_sample_t(golden, tag):
 
 
 @pytest.mark.parametrize("tag", ["P0", "P1"])
-def test_tcg_gcnpose(golden, tag):
-    """GCNpose (uv -> xyz, no time embedding) on the tensor-core engine."""
+def test_gcnpose_default_engine(golden, tag):
+    """GCNpose (uv -> xyz) with the default engine setting: the split-precision tensor-core engine, within 1e-3 abs of the
+    reference (north_star; measured: fp32 level) -- and the fused lift (root-centre + concat, one launch)."""
     from _cases import build_pose
     cfg, adj, model, sd = build_pose(tag, golden)
     model = model.to(dev())
     uv = t(golden, f"{tag}.uv")
     mask = torch.ones(1, 1, 17, dtype=torch.bool)
     xyz = model(uv.to(dev()), mask.to(dev())).cpu()
-    assert model.engine() == "tcg" and model.last_launch()[4] == 3
+    assert model.forward_engine() == "tcx" and model.last_launch()[4] == 2
+    ref = t(golden, f"{tag}.xyz")
+    scale = max(1.0, ref.abs().max().item())
+    err = (xyz - ref).abs().max().item()
+    print(f"gcnpose {tag} / tcx: |xyz - ref|={err:.2e} scale={scale:.2f}")
+    assert err < 1e-3 and err < 2e-5 * scale
+    l0 = D._lib.launch_count()
+    u5 = model.lift(uv.to(dev()), mask.to(dev())).cpu()
+    assert D._lib.launch_count() - l0 == 1
+    want = torch.cat([uv, O.root_centre(ref)], dim=2)
+    assert u5.shape == want.shape and (u5 - want).abs().max().item() < 4e-5 * scale
+    assert torch.equal(u5[:, :, :2], uv) and (u5[:, 0, 2:] == 0).all()
+    for eng in ("fp32", "tcg"):       # the other engines reach the same result through a glue kernel
+        v5 = model.set_engine(eng).lift(uv.to(dev()), mask.to(dev())).cpu()
+        assert (v5 - want).abs().max().item() < (4e-5 if eng == "fp32" else 3e-2) * scale
+
+
+@pytest.mark.parametrize("tag", ["P0", "P1"])
+def test_tcg_gcnpose(golden, tag):
+    """GCNpose on the fp16-operand engine, selected explicitly (not the default for the lifter: its output is the xyz
+    handed to the sampler, undamped -- oracle/tc_emulation.py)."""
+    from _cases import build_pose
+    cfg, adj, model, sd = build_pose(tag, golden)
+    model = model.to(dev()).set_engine("tcg")
+    uv = t(golden, f"{tag}.uv")
+    mask = torch.ones(1, 1, 17, dtype=torch.bool)
+    xyz = model(uv.to(dev()), mask.to(dev())).cpu()
+    assert model.forward_engine() == "tcg" and model.last_launch()[4] == 3
     emu = E.gcnpose_forward_tcg(sd, adj, 5, 4, uv, mask)
     ref = t(golden, f"{tag}.xyz")
     scale = max(1.0, ref.abs().max().item())
@@ -233,3 +284,63 @@ def test_trace_diagnostic_is_monotonic_and_optional():
     assert (np.diff(t) > 0).all() and kind[0] == 0 and kind[1] == 1
     again = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
     assert torch.equal(plain, again)
+
+
+def test_fp16_operand_range_saturates_instead_of_nan():
+    """fp16 operand range of the tensor-core engines (documented limit): an activation beyond +-65504 (tcg)
+    or +-131008 (tcx: hi + lo) -- possible with a trained checkpoint, impossible to rule out without one -- SATURATES in
+    the fp32->fp16 conversion (cvt.rn.satfinite.f16x2.f32) instead of becoming inf and then inf - inf = NaN inside an MMA.
+    Below the limit the engines keep their relative accuracy; above it the result is clipped but finite (the fp32 engine
+    has no such limit)."""
+    adj = D.adj_mx_from_edges()
+    mask = torch.ones(1, 1, 17, dtype=torch.bool, device=dev())
+    x = O.synthetic_poses(40, seed=5).to(dev())
+    tt = torch.full((40,), 3.0, device=dev())
+    for gain, overflow in ((2.0e4, False), (4.0e5, True)):
+        torch.manual_seed(0)
+        model = D.FusedGCNdiff(adj, O.default_config())
+        with torch.no_grad():
+            model.gconv_input.weight.mul_(gain)          # residual stream ~ gain: the Chebyshev blocks read it as an fp16 operand
+        model = model.to(dev())
+        ref = model.set_engine("fp32")(x, mask, tt, 0)
+        big = model.set_engine("tcx")(x, mask, tt, 0)
+        eps = model.set_engine("tcg")(x, mask, tt, 0)
+        assert model.last_launch()[4] == 3
+        scale = ref.abs().max().item()
+        print(f"gain {gain:g}: |eps|max={scale:.3g} tcg rel err={(eps - ref).abs().max().item() / scale:.2e} tcx rel err={(big - ref).abs().max().item() / scale:.2e}")
+        assert torch.isfinite(ref).all() and torch.isfinite(eps).all() and torch.isfinite(big).all()
+        if not overflow:
+            assert (eps - ref).abs().max().item() < 5e-3 * scale
+            assert (big - ref).abs().max().item() < 2e-5 * scale
+        out = D.generalized_steps(x, mask, [0, 12], model, betas())[0][-1]      # the sampler on the saturating engine: finite
+        assert torch.isfinite(out).all()
+
+
+def test_check_weights_sees_data_writes():
+    """`param.data.copy_()` (the reference's EMAHelper.ema idiom, models/ema.py:27-29) bumps no version counter: the
+    packed copy goes stale silently unless repack() is called.  check_weights() detects it; the package's EMAHelper
+    repacks by itself."""
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config()).to(dev()).eval()
+    x = O.synthetic_poses(32, seed=2).to(dev())
+    a = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert model.check_weights()
+    ema = D.EMAHelper(mu=0.9)
+    ema.register(model)
+    for k in ema.shadow:
+        ema.shadow[k] = ema.shadow[k] * 0.9
+    w = model.atten_layers[2].self_attn.linears[1].weight
+    w.data.copy_(w.data * 0.5)                          # invisible to the fingerprint ...
+    b = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert torch.equal(a, b)                            # ... so the stale copy is still in use (documented behaviour)
+    assert not model.check_weights()                    # detected, and repacked
+    c = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert (c - a).abs().max().item() > 1e-6 and model.check_weights()
+    ema.ema(model)                                      # the drop-in helper invalidates the packed copy itself
+    d = D.generalized_steps(x, None, [0, 12], model, betas())[0][-1]
+    assert (d - c).abs().max().item() > 1e-6 and model.check_weights()
+    # a deep copy owns its own native handle
+    import copy
+    m2 = copy.deepcopy(model)
+    e = D.generalized_steps(x, None, [0, 12], m2, betas())[0][-1]
+    assert torch.equal(d, e) and m2._handle is not model._handle and m2._handle.value != model._handle.value

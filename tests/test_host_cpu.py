@@ -111,12 +111,17 @@ def test_shard_range_partitions():
 
 
 def test_abi_library_exports_header_symbols():
-    """The C-ABI library loads without a GPU and exports every function include/diffpose_b200.h declares."""
-    header = open(os.path.join(ROOT, "include", "diffpose_b200.h")).read()
-    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    declared = set(re.findall(r"\b(dp_[a-z_0-9]+)\s*\(", header))
-    assert {"dp_create", "dp_pack", "dp_forward", "dp_sample", "dp_metrics", "dp_destroy", "dp_last_error"} <= declared
-    assert declared == set(_lib.SIGNATURES), "binding table and header disagree"
+    """The C-ABI library loads without a GPU and exports every function include/diffpose_b200.h (product ABI) and
+    include/diffpose_b200_diag.h (diagnostics, kept apart) declare."""
+    def names(fname):
+        header = open(os.path.join(ROOT, "include", fname)).read()
+        header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+        return set(re.findall(r"\b(dp_[a-z_0-9]+)\s*\(", header))
+    product, diag = names("diffpose_b200.h"), names("diffpose_b200_diag.h")
+    assert {"dp_create", "dp_pack", "dp_forward", "dp_lift", "dp_sample", "dp_metrics", "dp_destroy", "dp_last_error"} <= product
+    assert diag == {"dp_selftest_umma", "dp_selftest_umma_ts", "dp_selftest_cycles", "dp_set_trace"} and not (diag & product)
+    declared = product | diag
+    assert declared == set(_lib.SIGNATURES), "binding table and headers disagree"
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), f"{name} missing from libdiffpose_b200.so"
@@ -170,3 +175,46 @@ def test_step_scalars_are_cached_per_schedule():
     b.mul_(1.5)
     s3 = S.cached_ddim_steps(b, [0, 12], 0.0)
     assert s3 is not s1 and s3[0].sqrt_at != s1[0].sqrt_at
+
+
+def test_ema_helper_and_copies_keep_no_stale_state():
+    """The reference's EMAHelper.ema() writes parameters through `param.data.copy_` (models/ema.py:27-29), which bumps no
+    autograd version counter -- so the package ships an EMAHelper that calls repack() itself.  Also: deepcopy / pickling a
+    module must not share or carry the native handle."""
+    import copy
+    import pickle
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(5)
+    m = D.FusedGCNdiff(adj, O.default_config())
+    p = m.atten_layers[2].self_attn.linears[1].weight
+    v0 = p._version
+    p.data.copy_(p.data * 2)                       # the idiom in question: invisible to _version
+    assert p._version == v0
+    ema = D.EMAHelper(mu=0.5)
+    ema.register(m)
+    with torch.no_grad():
+        for q in m.parameters():
+            q.add_(1.0)
+    ema.update(m)                                   # shadow = 0.5 * (w + 1) + 0.5 * w
+    m._packed_version = ("sentinel",)               # pretend the weights are packed
+    ema.ema(m)
+    assert m._packed_version is None, "EMAHelper.ema() must invalidate the packed device copy"
+    want = p.detach().clone()
+    m2 = ema.ema_copy(torch.nn.DataParallel(m))
+    assert isinstance(m2, torch.nn.DataParallel) and torch.equal(m2.module.atten_layers[2].self_attn.linears[1].weight, want)
+    assert set(ema.state_dict()) == {k for k, _ in m.named_parameters()}
+    m._handle = "native pointer"
+    c = copy.deepcopy(m)
+    assert c._handle is None and c._packed_version is None and m._handle == "native pointer"
+    assert torch.equal(c.gconv_input.weight, m.gconv_input.weight) and c.gconv_input.weight is not m.gconv_input.weight
+    c2 = pickle.loads(pickle.dumps(m))
+    assert c2._handle is None and torch.equal(c2.gconv_output.bias, m.gconv_output.bias)
+    m._handle = None
+
+
+def test_engine_names():
+    m = D.FusedGCNpose(D.adj_mx_from_edges(), O.default_config(coords_dim=[2, 3]))
+    for name in ("auto", "fp32", "tcx", "tcg"):
+        m.set_engine(name)
+    with pytest.raises(KeyError):
+        m.set_engine("tc")                          # the first tensor-core engine is retired
