@@ -477,6 +477,97 @@ int dp_set_trace(dp_handle h, long long* dev_buf, int capacity) {
   return DP_OK;
 }
 
+// ---------------------------------------------------------------------------------------------- host-resident batches
+struct dp_hstream {
+  dp_handle h = nullptr;
+  long max_pose = 0;
+  int n_hyp = 1, mean = 0, depth = 0, head = 0;
+  size_t in_floats = 0, out_floats = 0;
+  cudaStream_t s_in = nullptr, s_out = nullptr;
+  std::vector<float*> x_dev, out_dev;
+  std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
+};
+
+int dp_hstream_create(dp_hstream_t* out, dp_handle h, long max_pose, int n_hyp, int mean_over_hyp, int depth) {
+  DP_REQUIRE(out && h, "dp_hstream_create: NULL argument");
+  *out = nullptr;
+  DP_REQUIRE(max_pose >= 1 && n_hyp >= 1 && depth >= 1 && depth <= 16, "dp_hstream_create: max_pose >= 1, n_hyp >= 1, 1 <= depth <= 16 required");
+  DP_REQUIRE(h->d.has_temb, "dp_hstream_create: the handle must be a GCNdiff denoiser (the sampler runs on it)");
+  DP_TRY(check_device(h, "dp_hstream_create"));
+  dp_hstream* s = new (std::nothrow) dp_hstream();
+  DP_REQUIRE(s != nullptr, "dp_hstream_create: out of host memory");
+  s->h = h; s->max_pose = max_pose; s->n_hyp = n_hyp; s->mean = (mean_over_hyp && n_hyp > 1) ? 1 : 0; s->depth = depth;
+  const size_t row = (size_t)h->d.n_pts * h->d.c_in;
+  s->in_floats = (size_t)max_pose * row;
+  s->out_floats = (size_t)max_pose * (s->mean ? 1 : n_hyp) * row;
+  cudaError_t e = cudaStreamCreateWithFlags(&s->s_in, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&s->s_out, cudaStreamNonBlocking);
+  for (int i = 0; i < depth && e == cudaSuccess; ++i) {
+    float *a = nullptr, *b = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
+    e = cudaMalloc(reinterpret_cast<void**>(&a), s->in_floats * sizeof(float));
+    if (e == cudaSuccess) { s->x_dev.push_back(a); e = cudaMalloc(reinterpret_cast<void**>(&b), s->out_floats * sizeof(float)); }
+    if (e == cudaSuccess) { s->out_dev.push_back(b); e = cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); }
+    if (e == cudaSuccess) { s->ev_in.push_back(e0); e = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming); }
+    if (e == cudaSuccess) { s->ev_done.push_back(e1); e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming); }
+    if (e == cudaSuccess) s->ev_out.push_back(e2);
+  }
+  if (e != cudaSuccess) {
+    set_error(std::string("dp_hstream_create: ") + cudaGetErrorString(e));
+    dp_hstream_destroy(s);
+    return DP_ERR_CUDA;
+  }
+  *out = s;
+  return DP_OK;
+}
+
+int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp_step* steps_host, int n_steps, const float* noise_dev,
+                      const unsigned char* mask_dev, float* out_host, void* stream, int* slot_out) {
+  DP_REQUIRE(s && x_host && out_host && steps_host && slot_out, "dp_hstream_submit: NULL argument");
+  DP_REQUIRE(n_pose >= 1 && n_pose <= s->max_pose, "dp_hstream_submit: batch exceeds the max_pose this stream was created for");
+  DP_TRY(check_device(s->h, "dp_hstream_submit"));
+  cudaStream_t cs = static_cast<cudaStream_t>(stream);
+  const int k = s->head;
+  const size_t row = (size_t)s->h->d.n_pts * s->h->d.c_in;
+  const size_t in_bytes = (size_t)n_pose * row * sizeof(float), out_bytes = (size_t)n_pose * (s->mean ? 1 : s->n_hyp) * row * sizeof(float);
+  // H2D on the copy-in stream, once the kernel that last read this slot's input has finished
+  DP_CUDA(cudaStreamWaitEvent(s->s_in, s->ev_done[k], 0));
+  DP_CUDA(cudaMemcpyAsync(s->x_dev[k], x_host, in_bytes, cudaMemcpyHostToDevice, s->s_in));
+  DP_CUDA(cudaEventRecord(s->ev_in[k], s->s_in));
+  // the sampler on the caller's stream, once the input is there and the slot's previous result has left the device
+  DP_CUDA(cudaStreamWaitEvent(cs, s->ev_in[k], 0));
+  DP_CUDA(cudaStreamWaitEvent(cs, s->ev_out[k], 0));
+  DP_TRY(dp_sample(s->h, s->x_dev[k], 0, s->out_dev[k], n_pose, s->n_hyp, steps_host, n_steps, noise_dev, mask_dev, s->mean, stream));
+  DP_CUDA(cudaEventRecord(s->ev_done[k], cs));
+  // D2H on the copy-out stream
+  DP_CUDA(cudaStreamWaitEvent(s->s_out, s->ev_done[k], 0));
+  DP_CUDA(cudaMemcpyAsync(out_host, s->out_dev[k], out_bytes, cudaMemcpyDeviceToHost, s->s_out));
+  DP_CUDA(cudaEventRecord(s->ev_out[k], s->s_out));
+  *slot_out = k;
+  s->head = (k + 1) % s->depth;
+  return DP_OK;
+}
+
+int dp_hstream_wait(dp_hstream_t s, int slot) {
+  DP_REQUIRE(s && slot >= 0 && slot < s->depth, "dp_hstream_wait: bad slot");
+  DP_CUDA(cudaEventSynchronize(s->ev_out[slot]));
+  return DP_OK;
+}
+
+void dp_hstream_destroy(dp_hstream_t s) {
+  if (!s) return;
+  if (s->s_in) cudaStreamSynchronize(s->s_in);
+  if (s->s_out) cudaStreamSynchronize(s->s_out);
+  for (float* p : s->x_dev) cudaFree(p);
+  for (float* p : s->out_dev) cudaFree(p);
+  for (cudaEvent_t e : s->ev_in) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_done) cudaEventDestroy(e);
+  for (cudaEvent_t e : s->ev_out) cudaEventDestroy(e);
+  if (s->s_in) cudaStreamDestroy(s->s_in);
+  if (s->s_out) cudaStreamDestroy(s->s_out);
+  delete s;
+}
+
 long dp_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int dp_last_launch_info(dp_handle h, long* out6) {

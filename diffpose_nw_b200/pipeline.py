@@ -70,77 +70,91 @@ def reduce_metrics(sums, group=None):
 class HostStream:
     """Batches that live in HOST memory, sampled at device speed: the H2D copy of batch i+1 and the D2H copy of
     batch i-1 run on their own CUDA streams while batch i is in the sampler kernel (the reference's loop,
-    runners/diffpose_frame.py:330-366, copies, computes and reads back strictly one after the other).
+    runners/diffpose_frame.py:330-366, copies, computes and reads back strictly one after the other).  The ring itself --
+    device buffers, copy streams, events, the three enqueues per batch -- lives in the C library (`dp_hstream_*`,
+    include/diffpose_b200.h); one `submit` is one C call.
 
         hs = HostStream(model_diff, batch=1024, seq=seq, betas=betas, test_times=1)
         for uvxyz_cpu in loader:            # pinned [B,17,5] fp32 tensors
             done = hs.submit(uvxyz_cpu)     # -> the result of an EARLIER batch (pinned host tensor) or None
         for out in hs.drain(): ...
 
-    Results come back in submission order.  `depth` batches are in flight; every buffer is allocated once.
+    Results come back in submission order.  `depth` batches are in flight; every buffer is allocated once.  A returned
+    tensor aliases a ring buffer and stays valid for the next `depth` submits.
     """
 
     def __init__(self, model_diff, batch, seq, betas, eta=0.0, test_times=1, src_mask=None, depth=3, device=None):
+        import collections
+        import ctypes
+        from . import _lib
         from .sampler import ddim_steps
         self.model = getattr(model_diff, "module", model_diff)
         self.dev = torch.device(device) if device is not None else self.model._device()
         if self.dev.type != "cuda":
             raise RuntimeError("HostStream needs the model on a CUDA device (diffpose_nw_b200 has no CPU path)")
-        self.B, self.H, self.seq, self.betas, self.eta, self.mask = batch, test_times, seq, betas, eta, src_mask
+        self.B, self.H, self.depth = batch, test_times, depth
         self.steps = ddim_steps(betas, seq, eta)
-        self.depth = depth
+        self.T = len(self.steps)
+        if any(s.c1 != 0.0 for s in self.steps):
+            raise RuntimeError("HostStream draws no noise: use eta = 0, or call sample() with noise= per batch")
+        self.model._ensure_packed(self.dev)
+        self._lib = _lib.load()
+        self._mask = self.model._mask_bytes(src_mask, self.dev)
+        self._mask_ptr = self._mask.data_ptr() if self._mask is not None else None
         c = self.model._c_in
-        self.x_dev = [torch.empty(batch, 17, c, device=self.dev) for _ in range(depth)]
-        self.out_host = [torch.empty(batch, 17, c).pin_memory() for _ in range(depth)]
-        self.out_dev = [None] * depth
-        self.s_in, self.s_out = torch.cuda.Stream(self.dev), torch.cuda.Stream(self.dev)
-        self.ev_in = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_done = [torch.cuda.Event() for _ in range(depth)]
-        self.ev_out = [torch.cuda.Event() for _ in range(depth)]
-        self.n_rows = [0] * depth
-        self.head = 0          # next slot to fill
-        self.inflight = 0
+        self.hs = ctypes.c_void_p()
+        with torch.cuda.device(self.dev):
+            _lib.check(self._lib.dp_hstream_create(ctypes.byref(self.hs), self.model._handle, batch, test_times, 1 if test_times > 1 else 0, depth),
+                       "dp_hstream_create")
+        self._handle_used = self.model._handle
+        self.out_host = [torch.empty(batch, 17, c).pin_memory() for _ in range(2 * depth)]
+        self._hpos = 0
+        self._slot = ctypes.c_int(0)
+        self._slot_ref = ctypes.byref(self._slot)
+        self._pending = collections.deque()        # (slot, host buffer, rows, input tensor kept alive until its copy has run)
 
-    def _collect(self, slot):
-        self.ev_out[slot].synchronize()
-        return self.out_host[slot][: self.n_rows[slot]]
+    def _collect(self):
+        slot, hb, n, _ = self._pending.popleft()
+        rc = self._lib.dp_hstream_wait(self.hs, slot)
+        if rc != 0:
+            from . import _lib
+            _lib.check(rc, "dp_hstream_wait")
+        return self.out_host[hb][:n]
 
     def submit(self, x_host):
-        """Queue one pinned host batch [n<=B,17,c].  Returns the oldest finished result when the ring is full, else None."""
-        ret = None
-        slot = self.head
-        if self.inflight == self.depth:
-            ret = self._collect(slot).clone()
-            self.inflight -= 1
+        """Queue one pinned host batch [n<=B,17,c] (fp32, contiguous).  Returns the oldest finished result when the ring is
+        full, else None."""
         n = x_host.shape[0]
         if n > self.B:
             raise RuntimeError(f"batch of {n} poses exceeds the {self.B} this HostStream was built for")
-        self.n_rows[slot] = n
-        cur = torch.cuda.current_stream(self.dev)
-        with torch.cuda.stream(self.s_in):
-            self.s_in.wait_event(self.ev_done[slot])          # the kernel that last read this input buffer is finished
-            self.x_dev[slot][:n].copy_(x_host, non_blocking=True)
-            self.ev_in[slot].record(self.s_in)
-        cur.wait_event(self.ev_in[slot])
-        cur.wait_event(self.ev_out[slot])                     # the previous result of this slot has left the device
-        out = sample(self.model, self.x_dev[slot][:n], self.mask, self.seq, self.betas, eta=self.eta, n_hyp=self.H,
-                     repeat_input=True, mean_over_hyp=self.H > 1, steps=self.steps)
-        self.out_dev[slot] = out                              # keep the tensor alive until its copy has run
-        self.ev_done[slot].record(cur)
-        with torch.cuda.stream(self.s_out):
-            self.s_out.wait_event(self.ev_done[slot])
-            self.out_host[slot][:n].copy_(out, non_blocking=True)
-            self.ev_out[slot].record(self.s_out)
-        self.head = (slot + 1) % self.depth
-        self.inflight += 1
+        if x_host.is_cuda or x_host.dtype is not torch.float32 or not x_host.is_contiguous():
+            raise RuntimeError("HostStream.submit takes a contiguous fp32 HOST tensor (pinned for overlap)")
+        if self.model._handle is not self._handle_used:
+            raise RuntimeError("the model was moved or re-created after this HostStream was built: build a new one")
+        self.model._ensure_packed(self.dev)           # weights edited since the last batch are re-packed (same rules as sample())
+        ret = self._collect() if len(self._pending) == self.depth else None
+        hb = self._hpos
+        self._hpos = (hb + 1) % len(self.out_host)
+        stream = torch.cuda.current_stream(self.dev).cuda_stream
+        rc = self._lib.dp_hstream_submit(self.hs, x_host.data_ptr(), n, self.steps, self.T, None, self._mask_ptr,
+                                         self.out_host[hb].data_ptr(), stream, self._slot_ref)
+        if rc != 0:
+            from . import _lib
+            _lib.check(rc, "dp_hstream_submit")
+        self._pending.append((self._slot.value, hb, n, x_host))
         return ret
 
     def drain(self):
         """Wait for and return (in order) the results still in flight; the returned tensors alias the ring buffers."""
         outs = []
-        slot = (self.head - self.inflight) % self.depth
-        while self.inflight:
-            outs.append(self._collect(slot))
-            slot = (slot + 1) % self.depth
-            self.inflight -= 1
+        while self._pending:
+            outs.append(self._collect())
         return outs
+
+    def __del__(self):
+        try:
+            if getattr(self, "hs", None) is not None and self.hs.value:
+                self._lib.dp_hstream_destroy(self.hs)
+                self.hs = None
+        except Exception:
+            pass

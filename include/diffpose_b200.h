@@ -134,6 +134,26 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
               const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
               int mean_over_hyp, void* stream);
 
+/* Batches that live in HOST memory.  Replaces the copy-in / sample / copy-out sequence of the evaluation loop
+ * (runners/diffpose_frame.py:333-335 `input_2d.to(self.device)` ..., :365 generalized_steps, :387 `.cpu()`), which the
+ * reference runs strictly one after the other, by a ring of `depth` slots: the host->device copy of batch i+1 and the
+ * device->host copy of batch i-1 run on the library's own copy streams while batch i is in the sampler kernel.
+ *   create : device buffers, two copy streams and the events of `depth` slots for batches of up to max_pose poses,
+ *            n_hyp hypotheses per pose (kernel-side repeat), optionally averaged (mean_over_hyp) -- all allocation
+ *            happens here, none per batch;
+ *   submit : x_host [n_pose,n_pts,c] and out_host ([n_pose*n_hyp,...] or [n_pose,...] with the mean) should be PINNED
+ *            host memory (pageable memory works but serialises); enqueues copy-in, dp_sample on `stream`, copy-out and
+ *            returns immediately; *slot identifies the batch.  noise_dev / mask_dev as in dp_sample (device, optional).
+ *            A slot is reused after `depth` submits: wait for its result before that.
+ *   wait   : blocks the host until the result of `slot` is in its out_host.
+ * Results complete in submission order. */
+typedef struct dp_hstream* dp_hstream_t;
+int dp_hstream_create(dp_hstream_t* out, dp_handle h, long max_pose, int n_hyp, int mean_over_hyp, int depth);
+int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp_step* steps_host, int n_steps, const float* noise_dev,
+                      const unsigned char* mask_dev, float* out_host, void* stream, int* slot);
+int dp_hstream_wait(dp_hstream_t s, int slot);
+void dp_hstream_destroy(dp_hstream_t s);
+
 /* Replaces mpjpe (common/loss.py:7-13) and p_mpjpe (common/loss.py:25-64, common/utils.py:155-187) as used
  * at runners/diffpose_frame.py:382-387: root-centres both inputs out of place, then accumulates
  * sums[0] += sum_pose mean_joint |pred-gt|, sums[1] += sum_pose P-MPJPE(pose), sums[2] += n.
