@@ -215,7 +215,8 @@ def run_reference(args, wl):
     sample = f"{n}-pose slice of the {wl['batch']}-pose batch per step, H={wl['n_hyp']}, T={len(wl['seq'])}, {steps} steps after {warm} warm-up"
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "poses/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": wl.get("scaling", "weak"), "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": bench_config(wl, int(os.environ.get("WORLD_SIZE", "1")))[0],
+            "data": "synthetic", "config": dict(bench_config(wl, int(os.environ.get("WORLD_SIZE", "1")))[0],
+                                                timing=f"{warm} warm-up steps, then {steps} timed steps (time.perf_counter)"),
             "detail": {"device": "host CPU", "torch_threads": torch.get_num_threads()},
             "cpu_baseline": {"value": val, "unit": "poses/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -334,11 +335,21 @@ def main():
     gc.disable()
     # untimed set-up before the W declared warm-up steps: ~10 ms of the same calls, so that the board has left its idle
     # power state when the (possibly only 2 ms long) timed window starts -- clocks are sampled and reported below
-    for i in range(100):
+    ramp = max(0, min(100, 200000 // max(1, B * H * T)))      # none for the long-step workloads
+    for i in range(ramp):
         out = step(args.steps + i)
     for i in range(args.warmup):
         out = step(args.steps + i)
     barrier()
+    # The barrier + synchronize leave the GPU idle (for milliseconds under NCCL), and its SM clock needs ~15 of these 0.1 ms
+    # steps to come back (tools/first_steps.py: 148, 111, 111, 108, ... 102 us per step after an idle gap).  A lead-in of
+    # untimed steps between the synchronisation and the first event hands the timed K steps a busy, full-clock GPU; the
+    # timed region itself is exactly K steps between two CUDA events, followed by barrier + synchronize.
+    lead_in = min(10, ramp)
+    for i in range(lead_in):
+        out = step(args.steps + args.warmup + i)
+    config["timing"] = (f"{ramp} set-up + {args.warmup} warm-up steps, barrier + synchronize, {lead_in} untimed lead-in steps, CUDA event, "
+                        f"{args.steps} timed steps, CUDA event, barrier + synchronize")
     l0 = _lib.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if sampler:

@@ -2,7 +2,8 @@
 //   hypothesis mean   runners/diffpose_frame.py:382
 //   mpjpe             common/loss.py:7-13 (after root-centring, runners/diffpose_frame.py:384-386)
 //   p_mpjpe           common/loss.py:25-64 == common/utils.py:155-187 (numpy float64 SVD in the reference;
-//                     here a one-sided Jacobi SVD of the 3x3 cross-covariance in fp64, one thread per pose)
+//                     here one warp per pose: fp64 shuffle reductions for the centring / cross-covariance, a one-sided
+//                     Jacobi SVD of the 3x3 matrix in fp32 registers, fp64 for the alignment error and the partial sums)
 #include "dp_internal.h"
 
 namespace dp {
@@ -20,41 +21,48 @@ __global__ void hyp_mean_kernel(const float* __restrict__ x, float* __restrict__
   }
 }
 
-__device__ inline void rot_cols(double a[3][3], int p, int q, double c, double s) {
+template <typename T>
+__device__ __forceinline__ void rot_cols(T a[3][3], int p, int q, T c, T s) {
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
-    const double ap = a[r][p], aq = a[r][q];
+    const T ap = a[r][p], aq = a[r][q];
     a[r][p] = c * ap - s * aq;
     a[r][q] = s * ap + c * aq;
   }
 }
 
 // H = U diag(sv) V^T with sv sorted descending; U, V orthogonal (U completed by a cross product when rank < 3).
-__device__ void svd3(const double h[3][3], double u[3][3], double sv[3], double v[3][3]) {
-  double a[3][3];
+// One-sided Jacobi, entirely in registers.  T = float: H is the cross-covariance of two unit-norm centred point sets
+// (entries <= 1), so an fp32 decomposition leaves the rotation accurate to ~2e-7 -- 1e-7 m on a pose -- against the 1e-6 m
+// the golden vectors are compared at; the sums that feed H and the final partial sums stay fp64.
+template <typename T>
+__device__ __forceinline__ void svd3(const T h[3][3], T u[3][3], T sv[3], T v[3][3]) {
+  const T kConv = sizeof(T) == 4 ? (T)6e-8 : (T)1e-15, kFloor = sizeof(T) == 4 ? (T)1e-37 : (T)1e-300, kRank = sizeof(T) == 4 ? (T)1e-6 : (T)1e-14;
+  const int kSweeps = sizeof(T) == 4 ? 12 : 30;
+  T a[3][3];
 #pragma unroll
   for (int i = 0; i < 3; ++i)
 #pragma unroll
-    for (int j = 0; j < 3; ++j) { a[i][j] = h[i][j]; v[i][j] = (i == j) ? 1.0 : 0.0; }
-  for (int sweep = 0; sweep < 30; ++sweep) {
-    double off = 0.0;
+    for (int j = 0; j < 3; ++j) { a[i][j] = h[i][j]; v[i][j] = (i == j) ? (T)1 : (T)0; }
+  for (int sweep = 0; sweep < kSweeps; ++sweep) {
+    T off = 0;
 #pragma unroll
     for (int pair = 0; pair < 3; ++pair) {
       const int p = pair == 2 ? 1 : 0, q = pair == 0 ? 1 : 2;
-      double alpha = 0, beta = 0, gamma = 0;
+      T alpha = 0, beta = 0, gamma = 0;
 #pragma unroll
       for (int r = 0; r < 3; ++r) { alpha += a[r][p] * a[r][p]; beta += a[r][q] * a[r][q]; gamma += a[r][p] * a[r][q]; }
-      const double lim = 1e-15 * sqrt(alpha * beta);
-      if (fabs(gamma) > lim && fabs(gamma) > 1e-300) {
+      const T lim = kConv * sqrt(alpha * beta);
+      if (fabs(gamma) > lim && fabs(gamma) > kFloor) {
         off += fabs(gamma);
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = (zeta >= 0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / sqrt(1.0 + t * t), s = c * t;
-        rot_cols(a, p, q, c, s);
-        rot_cols(v, p, q, c, s);
+        const T zeta = (beta - alpha) / ((T)2 * gamma);
+        const T t = (zeta >= 0 ? (T)1 : (T)-1) / (fabs(zeta) + sqrt((T)1 + zeta * zeta));
+        const T c = (T)1 / sqrt((T)1 + t * t), s = c * t;
+        rot_cols<T>(a, p, q, c, s);
+        rot_cols<T>(v, p, q, c, s);
       }
     }
-    if (off == 0.0) break;
+    if (off == (T)0) break;
   }
 #pragma unroll
   for (int j = 0; j < 3; ++j) sv[j] = sqrt(a[0][j] * a[0][j] + a[1][j] * a[1][j] + a[2][j] * a[2][j]);
@@ -63,7 +71,7 @@ __device__ void svd3(const double h[3][3], double u[3][3], double sv[3], double 
   for (int pass = 0; pass < 3; ++pass) {
     const int p = pass == 1 ? 1 : 0, q = p + 1;
     if (sv[p] < sv[q]) {
-      double t = sv[p]; sv[p] = sv[q]; sv[q] = t;
+      T t = sv[p]; sv[p] = sv[q]; sv[q] = t;
 #pragma unroll
       for (int r = 0; r < 3; ++r) {
         t = a[r][p]; a[r][p] = a[r][q]; a[r][q] = t;
@@ -71,7 +79,7 @@ __device__ void svd3(const double h[3][3], double u[3][3], double sv[3], double 
       }
     }
   }
-  const double tiny = 1e-14 * (sv[0] > 0 ? sv[0] : 1.0);
+  const T tiny = kRank * (sv[0] > 0 ? sv[0] : (T)1);
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
     if (sv[j] > tiny) {
@@ -80,11 +88,11 @@ __device__ void svd3(const double h[3][3], double u[3][3], double sv[3], double 
     }
   }
   if (sv[1] <= tiny) {  // rank <= 1: any unit vector orthogonal to u0
-    double ax = fabs(u[0][0]), ay = fabs(u[1][0]), az = fabs(u[2][0]);
-    double e[3] = {0, 0, 0};
-    e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = 1.0;
-    double w0 = u[1][0] * e[2] - u[2][0] * e[1], w1 = u[2][0] * e[0] - u[0][0] * e[2], w2 = u[0][0] * e[1] - u[1][0] * e[0];
-    const double n = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
+    T ax = fabs(u[0][0]), ay = fabs(u[1][0]), az = fabs(u[2][0]);
+    T e[3] = {0, 0, 0};
+    e[(ax <= ay && ax <= az) ? 0 : (ay <= az ? 1 : 2)] = (T)1;
+    T w0 = u[1][0] * e[2] - u[2][0] * e[1], w1 = u[2][0] * e[0] - u[0][0] * e[2], w2 = u[0][0] * e[1] - u[1][0] * e[0];
+    const T n = sqrt(w0 * w0 + w1 * w1 + w2 * w2);
     u[0][1] = w0 / n; u[1][1] = w1 / n; u[2][1] = w2 / n;
   }
   if (sv[2] <= tiny) {
@@ -94,7 +102,8 @@ __device__ void svd3(const double h[3][3], double u[3][3], double sv[3], double 
   }
 }
 
-__device__ inline double det3(const double m[3][3]) {
+template <typename T>
+__device__ __forceinline__ T det3(const T m[3][3]) {
   return m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]) - m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]) +
          m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
 }
@@ -157,15 +166,21 @@ __global__ void __launch_bounds__(kMetricWarps * 32) metrics_kernel(const float*
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b) h[a][b] = warp_sum_d((a0[a] / nx) * (b0[b] / ny));
-    double u[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, v[3][3], sv[3];
-    svd3(h, u, sv, v);
-    double r[3][3];
+    // rotation / scale in fp32 (see svd3): every lane runs the same decomposition on the same values
+    float hf[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) hf[a][b] = (float)h[a][b];
+    float u[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, v[3][3], sv[3];
+    svd3<float>(hf, u, sv, v);
+    float r[3][3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b) r[a][b] = v[a][0] * u[b][0] + v[a][1] * u[b][1] + v[a][2] * u[b][2];
-    const double dt = det3(r);
-    const double sg = dt > 0 ? 1.0 : (dt < 0 ? -1.0 : 0.0);
+    const float dt = det3<float>(r);
+    const float sg = dt > 0 ? 1.0f : (dt < 0 ? -1.0f : 0.0f);
 #pragma unroll
     for (int a = 0; a < 3; ++a) v[a][2] *= sg;
     sv[2] *= sg;
@@ -173,7 +188,7 @@ __global__ void __launch_bounds__(kMetricWarps * 32) metrics_kernel(const float*
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b) r[a][b] = v[a][0] * u[b][0] + v[a][1] * u[b][1] + v[a][2] * u[b][2];
-    const double scale = (sv[0] + sv[1] + sv[2]) * nx / ny;
+    const double scale = (double)(sv[0] + sv[1] + sv[2]) * nx / ny;
     double e = 0.0;
 #pragma unroll
     for (int b = 0; b < 3; ++b) {

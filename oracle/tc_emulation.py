@@ -1,8 +1,8 @@
 """CPU emulation of the tensor-core engine's ROUNDING POINTS (test infrastructure, like the rest of oracle/).
 
-The tcgen05 engine feeds fp16 operands (11-bit significand = TF32's) to the tensor cores and accumulates in fp32.
-This file restates GCNdiff.forward with a round-to-fp16 at exactly the places where the kernel stores an fp16
-operand, so that (a) the precision plan can be checked against the north_star tolerance before/without a GPU and
+The fast tcgen05 engine ("tcg", csrc/dp_tc2.cu) feeds fp16 operands (11-bit significand = TF32's) to the tensor cores
+and accumulates in fp32.  This file restates GCNdiff.forward with a round-to-fp16 at exactly the places where that
+kernel stores an fp16 operand, so that (a) the precision plan can be checked against the north_star tolerance before/without a GPU and
 (b) kernel bugs (indexing, layouts) can be told apart from precision effects: the kernel must agree with this
 emulation much more tightly (~1e-5) than with the fp32 oracle (~1e-4).
 """
@@ -23,55 +23,6 @@ def split16(b):
     """bias travels through the MMA as hi + lo fp16 (two columns of the constant-one K slab)."""
     hi = r16(b)
     return hi + r16(b - hi)
-
-
-def gcndiff_forward_tc(sd, adj, n_layer, n_head, x, mask, t):
-    hid = sd["gconv_input.weight"].shape[-1]
-    basis = O.cheb_basis(adj)
-    t1, t2 = basis[1], basis[2]
-    temb = O.timestep_embedding(t, hid)
-    temb = torch.nn.functional.linear(temb, sd["temb.dense.0.weight"], sd["temb.dense.0.bias"])
-    temb = torch.nn.functional.linear(O.swish(temb), sd["temb.dense.1.weight"], sd["temb.dense.1.bias"])
-
-    def cheb_in(v):       # fp32 input convolution (K = 15, SIMT)
-        return O.cheb_conv(v, adj, sd["gconv_input.weight"], sd["gconv_input.bias"])
-
-    def cheb_tc(v_x, v_t1, v_t2, w, b):
-        a = torch.cat([r16(v_x), r16(v_t1), r16(v_t2)], dim=-1)
-        wcat = r16(w.reshape(3 * w.shape[2], w.shape[3]))
-        return a @ wcat + split16(b.reshape(-1))
-
-    X = cheb_in(x)
-    d_k = hid // n_head
-    for l in range(n_layer):
-        p, g = f"atten_layers.{l}", f"gconv_layers.{l}"
-        # attention sublayer
-        a = r16(O.layer_norm(X, sd[f"{p}.sublayer.0.norm.a_2"], sd[f"{p}.sublayer.0.norm.b_2"]))
-        q, k, v = [r16(a @ r16(sd[f"{p}.self_attn.linears.{i}.weight"]).T + split16(sd[f"{p}.self_attn.linears.{i}.bias"]))
-                   for i in range(3)]
-        nb = X.shape[0]
-        qh, kh, vh = [z.view(nb, -1, n_head, d_k).transpose(1, 2) for z in (q, k, v)]
-        sc = torch.matmul(qh, kh.transpose(-2, -1)) / math.sqrt(d_k)
-        if mask is not None:
-            sc = sc.masked_fill(mask.unsqueeze(1) == 0, -1e9)
-        o = torch.matmul(torch.softmax(sc, dim=-1), vh).transpose(1, 2).contiguous().view(nb, -1, hid)
-        X = X + (r16(o) @ r16(sd[f"{p}.self_attn.linears.3.weight"]).T + split16(sd[f"{p}.self_attn.linears.3.bias"]))
-        # GraphNet sublayer, fc2 and the second aggregation commuted
-        a_hat = sd[f"{p}.feed_forward.A_hat"]
-        dd = (a_hat.sum(0) + 1e-5) ** (-0.5)
-        lhat = dd.view(-1, 1) * a_hat * dd.view(1, -1)
-        y = O.layer_norm(X, sd[f"{p}.sublayer.1.norm.a_2"], sd[f"{p}.sublayer.1.norm.b_2"])
-        a = r16(torch.matmul(lhat, y))
-        h = torch.relu(a @ r16(sd[f"{p}.feed_forward.gconv1.fc.weight"]).T + split16(sd[f"{p}.feed_forward.gconv1.fc.bias"]))
-        z = r16(h) @ r16(sd[f"{p}.feed_forward.gconv2.fc.weight"]).T
-        X = X + torch.matmul(lhat, z) + sd[f"{p}.feed_forward.gconv2.fc.bias"]
-        # residual Chebyshev block
-        h1 = torch.relu(cheb_tc(X, torch.matmul(t1, X), torch.matmul(t2, X), sd[f"{g}.gconv1.gconv.weight"], sd[f"{g}.gconv1.gconv.bias"]))
-        h1 = h1 + torch.nn.functional.linear(O.swish(temb), sd[f"{g}.temb_proj.weight"], sd[f"{g}.temb_proj.bias"])[:, None, :]
-        h1 = r16(h1)     # the kernel keeps this hidden activation only as the fp16 operand
-        h2 = torch.relu(cheb_tc(h1, torch.matmul(t1, h1), torch.matmul(t2, h1), sd[f"{g}.gconv2.gconv.weight"], sd[f"{g}.gconv2.gconv.bias"]))
-        X = X + h2
-    return O.cheb_conv(X, adj, sd["gconv_output.weight"], sd["gconv_output.bias"])
 
 
 def gcnpose_forward_tcg(sd, adj, n_layer, n_head, x, mask, p16=True):
