@@ -2,8 +2,8 @@
 //   hypothesis mean   runners/diffpose_frame.py:382
 //   mpjpe             common/loss.py:7-13 (after root-centring, runners/diffpose_frame.py:384-386)
 //   p_mpjpe           common/loss.py:25-64 == common/utils.py:155-187 (numpy float64 SVD in the reference;
-//                     here one warp per pose: fp64 shuffle reductions for the centring / cross-covariance, a one-sided
-//                     Jacobi SVD of the 3x3 matrix in fp32 registers, fp64 for the alignment error and the partial sums)
+//                     here one warp per pose: fp32 shuffle reductions for the centring / cross-covariance, a one-sided
+//                     Jacobi SVD of the 3x3 matrix in fp32 registers, fp64 for the partial sums over poses)
 #include "dp_internal.h"
 
 namespace dp {
@@ -108,15 +108,15 @@ __device__ __forceinline__ T det3(const T m[3][3]) {
          m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
 }
 
-__device__ __forceinline__ double warp_sum_d(double v) {
+__device__ __forceinline__ float warp_sum_f(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
 
 // One WARP per pose: lane j < 17 owns joint j of the prediction and the target; every per-pose sum is a warp shuffle
-// reduction (fp64, like the reference's numpy), and the 3x3 SVD -- a register-only Jacobi iteration -- runs redundantly
-// on all lanes (no divergence, no local-memory arrays).  A block of 8 warps handles 8 poses, so 1024 poses already
+// reduction, and the 3x3 SVD -- a register-only Jacobi iteration -- runs redundantly on all lanes (no divergence, no
+// local-memory arrays).  A block of 8 warps handles 8 poses, so 1024 poses already
 // spread over 128 CTAs (the first version ran one thread per pose with 34x3 doubles of local memory on 8 CTAs: 44 us
 // per 1024 poses, half a sampler launch).
 constexpr int kMetricWarps = 8;
@@ -147,33 +147,34 @@ __global__ void __launch_bounds__(kMetricWarps * 32) metrics_kernel(const float*
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
     const double e1 = (double)(acc / (float)NP);
 
-    // p_mpjpe (common/loss.py:25-64): X = target, Y = prediction
-    double X[3], Y[3], mx[3], my[3];
+    // p_mpjpe (common/loss.py:25-64): X = target, Y = prediction.  All of it in fp32 registers + warp shuffles: coordinates
+    // are ~0.3 m, so fp32 centring / norms / cross-covariance are good to ~1e-7 and the aligned joint errors to ~1e-7 m,
+    // against the 1e-6 m the golden vectors are compared at and the 0.05 mm of the north-star tolerance; fp64 only for the
+    // sums over poses below.  (The first warp-per-pose version kept fp64 throughout: 15 dependent fp64 divisions / square
+    // roots and 18 two-word shuffle reductions per pose made it 14 us per 1024 poses.)
+    float X[3], Y[3], mx[3], my[3];
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { X[c] = live ? (double)gv[c] : 0.0; Y[c] = live ? (double)pv[c] : 0.0; }
+    for (int c = 0; c < 3; ++c) { X[c] = live ? gv[c] : 0.f; Y[c] = live ? pv[c] : 0.f; }
 #pragma unroll
-    for (int c = 0; c < 3; ++c) { mx[c] = warp_sum_d(X[c]) / NP; my[c] = warp_sum_d(Y[c]) / NP; }
-    double a0[3], b0[3], nx = 0.0, ny = 0.0;
+    for (int c = 0; c < 3; ++c) { mx[c] = warp_sum_f(X[c]) * (1.0f / NP); my[c] = warp_sum_f(Y[c]) * (1.0f / NP); }
+    float a0[3], b0[3], nx = 0.f, ny = 0.f;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      a0[c] = live ? X[c] - mx[c] : 0.0;
-      b0[c] = live ? Y[c] - my[c] : 0.0;
-      nx += a0[c] * a0[c]; ny += b0[c] * b0[c];
+      a0[c] = live ? X[c] - mx[c] : 0.f;
+      b0[c] = live ? Y[c] - my[c] : 0.f;
+      nx = fmaf(a0[c], a0[c], nx); ny = fmaf(b0[c], b0[c], ny);
     }
-    nx = sqrt(warp_sum_d(nx)); ny = sqrt(warp_sum_d(ny));
-    double h[3][3];                                         // H = X0^T Y0 of the normalised, centred point sets
+    nx = sqrtf(warp_sum_f(nx)); ny = sqrtf(warp_sum_f(ny));
+    const float inx = 1.0f / nx, iny = 1.0f / ny;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { a0[c] *= inx; b0[c] *= iny; }
+    float h[3][3];                                         // H = X0^T Y0 of the normalised, centred point sets
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
-      for (int b = 0; b < 3; ++b) h[a][b] = warp_sum_d((a0[a] / nx) * (b0[b] / ny));
-    // rotation / scale in fp32 (see svd3): every lane runs the same decomposition on the same values
-    float hf[3][3];
-#pragma unroll
-    for (int a = 0; a < 3; ++a)
-#pragma unroll
-      for (int b = 0; b < 3; ++b) hf[a][b] = (float)h[a][b];
+      for (int b = 0; b < 3; ++b) h[a][b] = warp_sum_f(a0[a] * b0[b]);
     float u[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}, v[3][3], sv[3];
-    svd3<float>(hf, u, sv, v);
+    svd3<float>(h, u, sv, v);
     float r[3][3];
 #pragma unroll
     for (int a = 0; a < 3; ++a)
@@ -188,16 +189,16 @@ __global__ void __launch_bounds__(kMetricWarps * 32) metrics_kernel(const float*
     for (int a = 0; a < 3; ++a)
 #pragma unroll
       for (int b = 0; b < 3; ++b) r[a][b] = v[a][0] * u[b][0] + v[a][1] * u[b][1] + v[a][2] * u[b][2];
-    const double scale = (double)(sv[0] + sv[1] + sv[2]) * nx / ny;
-    double e = 0.0;
+    const float scale = (sv[0] + sv[1] + sv[2]) * nx * iny;
+    float e = 0.f;
 #pragma unroll
     for (int b = 0; b < 3; ++b) {
-      const double tr = mx[b] - scale * (my[0] * r[0][b] + my[1] * r[1][b] + my[2] * r[2][b]);
-      const double al = scale * (Y[0] * r[0][b] + Y[1] * r[1][b] + Y[2] * r[2][b]) + tr;
-      const double df = al - X[b];
-      e += df * df;
+      // aligned = scale * Y R + t with t = muX - scale * muY R   <=>   scale * (Y - muY) R + muX
+      const float al = scale * ny * (b0[0] * r[0][b] + b0[1] * r[1][b] + b0[2] * r[2][b]) + mx[b];
+      const float df = al - X[b];
+      e = fmaf(df, df, e);
     }
-    const double e2 = warp_sum_d(live ? sqrt(e) : 0.0) / NP;
+    const double e2 = (double)(warp_sum_f(live ? sqrtf(e) : 0.f) * (1.0f / NP));
     e1s += e1; e2s += e2; cnt += 1.0;
     if (per_pose && lane == 0) { per_pose[2 * i] = (float)e1; per_pose[2 * i + 1] = (float)e2; }
   }
