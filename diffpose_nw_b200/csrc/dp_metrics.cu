@@ -123,6 +123,11 @@ constexpr int kMetricWarps = 8;
 __global__ void __launch_bounds__(kMetricWarps * 32) metrics_kernel(const float* __restrict__ pred, int ps, int po, const float* __restrict__ gt, long n,
                                                                     double* __restrict__ sums, float* __restrict__ per_pose) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // programmatic dependent launch (the evaluation loop alternates sampler and metrics kernels on one stream): this grid may
+  // have been launched while the sampler that produces `pred` was draining -- wait for its results, and let the next
+  // sampler launch begin its own set-up right away
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   double e1s = 0.0, e2s = 0.0, cnt = 0.0;      // this warp's partial sums (identical on every lane)
   for (long i = (long)blockIdx.x * kMetricWarps + warp; i < n; i += (long)gridDim.x * kMetricWarps) {
     const int j = lane < NP ? lane : 0;
@@ -234,7 +239,13 @@ int metrics_launch(const float* pred, int pred_stride, int pred_offset, const fl
   (void)n_pts;
   long grid = (n + kMetricWarps - 1) / kMetricWarps;
   if (grid > 148 * 8) grid = 148 * 8;
-  metrics_kernel<<<(unsigned)grid, kMetricWarps * 32, 0, s>>>(pred, pred_stride, pred_offset, gt, n, sums, per_pose);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(kMetricWarps * 32); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  DP_CUDA(cudaLaunchKernelEx(&cfg, metrics_kernel, pred, pred_stride, pred_offset, gt, n, sums, per_pose));
   count_launch();
   DP_CUDA(cudaGetLastError());
   return DP_OK;

@@ -218,3 +218,27 @@ def test_engine_names():
         m.set_engine(name)
     with pytest.raises(KeyError):
         m.set_engine("tc")                          # the first tensor-core engine is retired
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` runs without a GPU, prints ONE JSON line with the contract's keys, and carries exactly the
+    `config` object the GPU arm prints for the same command line (the driver compares them)."""
+    import json
+    import subprocess
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "poses/s" and d["higher_is_better"] is True and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "poses/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["gpu_launches"] == 0 and d["steps"] == 1 and d["warmup"] == 3
+    assert d["config"] == bench.bench_config(bench.WORKLOADS["cpn1024"], 1)[0]
+    assert set(d["config"]) == {"workload", "batch", "batch_is", "n_hyp", "T", "eta", "l2"}
+    for name, wl in bench.WORKLOADS.items():      # every workload names a BASELINE config and a schedule inside the 51-entry beta table
+        assert "configs[" in wl["name"] and max(wl["seq"]) < 51 and wl["batch"] >= 1
