@@ -41,7 +41,7 @@ WORKLOADS = {
                     name="configs[1]: human36m_diffpose_uvxyz_cpn.yml shape, batch 1024, H=1, seq=[0,12] (T=2), random-init"),
     # the same batches through the evaluation loop of runners/diffpose_frame.py:365-387: sampler, then MPJPE / P-MPJPE partial sums
     "evalloop": dict(batch=1024, n_hyp=1, seq=list(range(0, 24, 12)), eta=0.0, with_metrics=True,
-                     name="configs[1] + metrics per batch: sampler (batch 1024, H=1, T=2) followed by dp_metrics (MPJPE, P-MPJPE) as diffpose_frame.py:365-387"),
+                     name="configs[1] + metrics per batch: sampler (batch 1024, H=1, T=2) with the MPJPE / P-MPJPE sums of the batch fused into its tail (dp_sample_eval), as diffpose_frame.py:365-387"),
     # BASELINE.json configs[2]: gt.yml shape (seq [0,6]), test_times=5, ONE batch of 1024 poses sharded over the ranks (strong scaling)
     "gt1024x5": dict(batch=1024, n_hyp=5, seq=[0, 6], eta=1.0, scaling="strong",
                      name="configs[2]: human36m_diffpose_uvxyz_gt.yml shape, batch 1024 sharded over the ranks, H=5 (fused mean), seq=[0,6] (T=2), eta=1 with device noise, random-init"),
@@ -306,11 +306,12 @@ def main():
         if pose_model is not None:
             out = D.lift_and_refine(model, model_pose=pose_model, input_2d=uv_pool[i % pool_n], src_mask=None, seq=seq, betas=betas,
                                     eta=eta, test_times=H)
+        elif wl.get("with_metrics"):      # sampler + MPJPE / P-MPJPE sums of the batch in one launch (dp_sample_eval)
+            out = D.sample(model, pool[i % pool_n], None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True,
+                           mean_over_hyp=(H > 1), steps=steps_arr, targets=targets, sums=msums)
         else:
             out = D.sample(model, pool[i % pool_n], None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True,
                            mean_over_hyp=(H > 1), steps=steps_arr)
-        if wl.get("with_metrics"):
-            D.pose_error_sums(out, targets, sums=msums)
         return out
 
     def barrier():
@@ -392,9 +393,8 @@ def main():
                 host_out[i & 1].copy_(o, non_blocking=True)
                 return
             xd.copy_(host_in[i & 1], non_blocking=True)
-            o = D.sample(model, xd, None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=(H > 1), steps=steps_arr)
-            if wl.get("with_metrics"):
-                D.pose_error_sums(o, targets, sums=msums)
+            o = D.sample(model, xd, None, seq, betas, eta=eta, noise=noise, n_hyp=H, repeat_input=True, mean_over_hyp=(H > 1), steps=steps_arr,
+                         targets=targets if wl.get("with_metrics") else None, sums=msums if wl.get("with_metrics") else None)
             host_out[i & 1].copy_(o, non_blocking=True)
 
         if wl.get("with_metrics"):

@@ -376,9 +376,9 @@ int dp_lift(dp_handle h, const float* uv, const unsigned char* mask, float* out_
   return lift_glue_launch(uv, h->lift_scratch, out_uvxyz, n, d.n_pts, d.c_in, d.c_out, s);
 }
 
-int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
-              const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
-              int mean_over_hyp, void* stream) {
+static int sample_impl(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+                       const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
+                       int mean_over_hyp, const float* targets, double* sums, void* stream) {
   DP_REQUIRE(h && x_in && x_out && steps_host, "dp_sample: NULL argument");
   DP_REQUIRE(n_pose >= 0 && n_hyp >= 1 && n_steps >= 1, "dp_sample: n_pose >= 0, n_hyp >= 1, n_steps >= 1 required");
   DP_REQUIRE(h->d.has_temb, "dp_sample: handle was created with has_temb = 0 (GCNpose has no sampler)");
@@ -424,8 +424,10 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
   }
 
   const int eng = dp_get_engine(h);
-  // default engine: the hypothesis mean is fused into the kernel's final store (one launch, no [H*B] scratch)
-  if (eng == DP_ENGINE_TCG) return tc2_sample(h, x_in, x_is_repeated, x_out, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, mean_over_hyp, s);
+  // default engine: the hypothesis mean -- and, for dp_sample_eval, the MPJPE / P-MPJPE sums -- are fused into the kernel's
+  // final store (one launch, no [H*B] scratch)
+  if (eng == DP_ENGINE_TCG)
+    return tc2_sample(h, x_in, x_is_repeated, x_out, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, mean_over_hyp, targets, sums, s);
   float* dst = x_out;
   const int row_floats = d.n_pts * d.c_out;
   if (mean_over_hyp && n_hyp > 1) {
@@ -439,7 +441,23 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
     rc = simt_sample(h, x_in, x_is_repeated, dst, n_pose, n_hyp, steps_dev, &inl, n_steps, noise, mask, s);
   if (rc != DP_OK) return rc;
   if (mean_over_hyp && n_hyp > 1) DP_TRY(hyp_mean_launch(dst, x_out, n_pose, n_hyp, row_floats, s));
+  if (targets != nullptr) DP_TRY(metrics_launch(x_out, d.c_out, d.c_out - 3, targets, n_pose, d.n_pts, sums, nullptr, s));
   return DP_OK;
+}
+
+int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+              const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
+              int mean_over_hyp, void* stream) {
+  return sample_impl(h, x_in, x_is_repeated, x_out, n_pose, n_hyp, steps_host, n_steps, noise, mask, mean_over_hyp, nullptr, nullptr, stream);
+}
+
+int dp_sample_eval(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+                   const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
+                   int mean_over_hyp, const float* targets_xyz, double* sums, void* stream) {
+  DP_REQUIRE(h && targets_xyz && sums, "dp_sample_eval: NULL argument");
+  DP_REQUIRE(h->d.c_out >= 3, "dp_sample_eval: the model's output needs at least the three xyz coordinates");
+  DP_REQUIRE(n_hyp == 1 || mean_over_hyp, "dp_sample_eval: with n_hyp > 1 the metrics are those of the hypothesis mean (set mean_over_hyp)");
+  return sample_impl(h, x_in, x_is_repeated, x_out, n_pose, n_hyp, steps_host, n_steps, noise, mask, mean_over_hyp, targets_xyz, sums, stream);
 }
 
 int dp_metrics(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,

@@ -143,9 +143,10 @@ int tc2_pack(dp_model* m, cudaStream_t s);
 int tc2_tau(dp_model* m, int n_steps, cudaStream_t s);
 void tc2_free(dp_model* m);
 // mean_over_hyp: x_out is [n_pose, n_pts, c], the hypothesis mean fused into the kernel's final store
+// gt / sums (optional): fused evaluation tail, see dp_sample_eval
 int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
                const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
-               const unsigned char* mask, int mean_over_hyp, cudaStream_t s);
+               const unsigned char* mask, int mean_over_hyp, const float* gt, double* sums, cudaStream_t s);
 // dp_metrics.cu
 int metrics_launch(const float* pred, int pred_stride, int pred_offset, const float* gt, long n, int n_pts,
                    double* sums, float* per_pose, cudaStream_t s);

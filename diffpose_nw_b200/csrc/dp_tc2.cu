@@ -34,6 +34,7 @@
 #include <cmath>
 #include "dp_internal.h"
 #include "dp_sm100.cuh"
+#include "dp_metrics_dev.cuh"
 
 namespace dp {
 
@@ -104,7 +105,9 @@ constexpr int OFF_STAT = al16(OFF_T12 + NP * NP * 8);      // LayerNorm partial 
 constexpr int OFF_MASK = OFF_STAT + 2 * TM * 8;            // key mask [32]
 constexpr int OFF_BAR = OFF_MASK + 128;                    // mbarriers: full[4], empty[4], pfull[2], pempty[2], (unused)[4], acc[4]
 constexpr int OFF_TMEM = OFF_BAR + 192;
-constexpr int SMEM_BYTES = OFF_TMEM + 16;
+constexpr int OFF_EV = OFF_TMEM + 16;                      // fused evaluation: xyz of the tile's finished poses [7][17][3] fp32, then their targets
+constexpr int EV_FLOATS = TP * NP * 3;
+constexpr int SMEM_BYTES = OFF_EV + 2 * EV_FLOATS * 4;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
 static_assert(OFF_W % 128 == 0 && OFF_ONES % 16 == 0 && OFF_JS % 16 == 0 && OFF_CS % 16 == 0 && OFF_MK % 16 == 0 && OFF_TALL % 16 == 0 && OFF_SIDE % 16 == 0 && OFF_A16 % 16 == 0 && OFF_BAR % 16 == 0 && OFF_T12 % 16 == 0 && OFF_XT % 16 == 0 &&
               OFF_STAT % 16 == 0 && OFF_PAR % 16 == 0 && OFF_TEP % 16 == 0 && PAR_BYTES % 16 == 0 && LP_BYTES % 16 == 0, "alignment");
@@ -139,6 +142,8 @@ struct Tc2Args {
   const float* noise;
   const unsigned char* mask;
   const dp_step* steps_dev;
+  const float* gt;           // fused evaluation (dp_sample_eval): targets [n_pose][17][3]; every finished pose (after the hypothesis
+  double* sums;              //   mean, if any) adds its MPJPE / P-MPJPE to sums[0..1] and 1 to sums[2] (common/loss.py, dp_metrics)
   long long* trace;          // optional diagnostic: CTA 0 records clock64() at every hand-over (see dp_set_trace)
   int trace_cap;
 };
@@ -744,6 +749,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
     uint8_t* const side2 = side0 ? side0 + 2 * SIDE_BYTES : nullptr;
 
     float macc = 0.f;     // mean_over_hyp: running hypothesis sum of output element `tid` of the pose being completed
+    double ev1 = 0.0, ev2 = 0.0, evn = 0.0;   // fused evaluation: this warp's partial sums (the same on every lane)
     for (int it = 0; it < my_tiles; ++it) {
       const long g0 = a.mean_over_hyp ? row_lo + (long)it * TP : ((long)blockIdx.x + (long)it * gridDim.x) * TP;
       const int npose = (int)min((long)TP, (a.mean_over_hyp ? row_hi : a.n_rows) - g0);
@@ -768,6 +774,15 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           if (a.mean_over_hyp) { const long b = g / a.n_hyp; src = a.x_is_repeated ? (g - b * a.n_hyp) * a.n_pose + b : b; }
           else src = a.x_is_repeated ? g : (g % a.n_pose);
           xt[(p * PS + rem / ci) * XS + rem % ci] = a.x_in[src * (NP * ci) + rem];
+        }
+      }
+      if (a.gt != nullptr) {        // targets of the poses this tile finishes: requested now, read in the tile's tail
+        float* evg = reinterpret_cast<float*>(smem + OFF_EV) + EV_FLOATS;
+        for (int idx = tid; idx < npose * NP * 3; idx += kComputeThreads) {
+          const int p = idx / (NP * 3);
+          const long g = g0 + p;
+          const long b = a.mean_over_hyp ? g / a.n_hyp : g % a.n_pose;
+          if (!a.mean_over_hyp || g - b * a.n_hyp == a.n_hyp - 1) evg[idx] = __ldg(a.gt + b * (NP * 3) + (idx - p * (NP * 3)));
         }
       }
       bar_compute();
@@ -996,16 +1011,53 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             const int h = (int)(g - b * a.n_hyp);
             const float v = src[p * PS * XS];
             macc = h == 0 ? __fadd_rn(0.f, v) : __fadd_rn(macc, v);
-            if (h == a.n_hyp - 1) a.out[(size_t)b * NP * co + tid] = __fdiv_rn(macc, (float)a.n_hyp);
+            if (h == a.n_hyp - 1) {
+              const float mval = __fdiv_rn(macc, (float)a.n_hyp);
+              a.out[(size_t)b * NP * co + tid] = mval;
+              if (a.gt != nullptr && tid % co >= co - 3) reinterpret_cast<float*>(smem + OFF_EV)[p * (NP * 3) + (tid / co) * 3 + tid % co - (co - 3)] = mval;
+            }
           }
         }
       } else if (!a.forward_only) {
         for (int idx = tid; idx < nval; idx += kComputeThreads) {
           const int p = idx / (NP * co), rem = idx - p * (NP * co);
-          a.out[(size_t)g0 * NP * co + idx] = xt[(p * PS + rem / co) * XS + rem % co];
+          const float xv = xt[(p * PS + rem / co) * XS + rem % co];
+          a.out[(size_t)g0 * NP * co + idx] = xv;
+          if (a.gt != nullptr && rem % co >= co - 3) reinterpret_cast<float*>(smem + OFF_EV)[p * (NP * 3) + (rem / co) * 3 + rem % co - (co - 3)] = xv;
+        }
+      }
+      if (a.gt != nullptr) {
+        // Fused evaluation tail (runners/diffpose_frame.py:382-387): one warp per finished pose of this tile -- at most 7, on 8
+        // compute warps -- computes MPJPE and P-MPJPE from the xyz just stored and the targets requested at the tile's start.
+        bar_compute();
+        const float* evp = reinterpret_cast<const float*>(smem + OFF_EV);
+        int cnt = 0;
+        for (int p = 0; p < npose; ++p) {
+          const long g = g0 + p;
+          if (a.mean_over_hyp && g % a.n_hyp != a.n_hyp - 1) continue;
+          if ((cnt & 7) == warp) {
+            const int j = lane < NP ? lane : 0;
+            float pv[3], gv[3];
+#pragma unroll
+            for (int cc = 0; cc < 3; ++cc) { pv[cc] = evp[p * (NP * 3) + j * 3 + cc]; gv[cc] = evp[EV_FLOATS + p * (NP * 3) + j * 3 + cc]; }
+            float e1, e2;
+            metric::pose_errors(pv, gv, lane, e1, e2);
+            ev1 += (double)e1; ev2 += (double)e2; evn += 1.0;
+          }
+          ++cnt;
         }
       }
       bar_compute();
+    }
+    if (a.gt != nullptr) {     // one atomic per CTA and quantity
+      double* red = reinterpret_cast<double*>(smem + OFF_STAT);      // [3][8], free after the last tile
+      if (lane == 0) { red[warp] = ev1; red[8 + warp] = ev2; red[16 + warp] = evn; }
+      bar_compute();
+      if (tid < 3) {
+        double sacc = 0.0;
+        for (int wq = 0; wq < kComputeThreads / 32; ++wq) sacc += red[tid * 8 + wq];
+        if (sacc != 0.0) atomicAdd(a.sums + tid, sacc);
+      }
     }
   }
   if (ktrace) ktrace[2] = clock64();
@@ -1226,8 +1278,9 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
 
 int tc2_sample(dp_model* m, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
                const dp_step* steps_dev, const StepsArg* inl, int n_steps, const float* noise,
-               const unsigned char* mask, int mean_over_hyp, cudaStream_t s) {
+               const unsigned char* mask, int mean_over_hyp, const float* gt, double* sums, cudaStream_t s) {
   Tc2Args a{};
+  a.gt = gt; a.sums = sums;
   a.x_in = x_in; a.x_is_repeated = x_is_repeated; a.out = x_out;
   a.n_rows = n_pose * n_hyp; a.n_pose = n_pose; a.n_hyp = n_hyp; a.mean_over_hyp = (mean_over_hyp && n_hyp > 1) ? 1 : 0;
   a.n_steps = n_steps; a.noise = noise; a.mask = mask;

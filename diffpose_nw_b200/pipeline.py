@@ -23,15 +23,16 @@ def shard_range(n, rank, world):
 
 
 def lift_and_refine(model_diff, x_uvxyz=None, *, model_pose=None, input_2d=None, src_mask=None, seq, betas, eta=0.0,
-                    test_times=1, noise=None):
+                    test_times=1, noise=None, targets=None, sums=None):
     """Two-stage inference for one batch.  Give either `x_uvxyz` [B,17,5] or (`model_pose`, `input_2d` [B,17,2]).
-    Returns the hypothesis-averaged uvxyz [B,17,5]."""
+    Returns the hypothesis-averaged uvxyz [B,17,5].  With `targets` [B,17,3] and `sums` (CUDA fp64 [3]) the MPJPE / P-MPJPE
+    partial sums of the batch are accumulated by the sampler launch itself (`dp_sample_eval`)."""
     if x_uvxyz is None:
         # lift + out-of-place root-centring (SURVEY.md 8a quirk 4) + concat in ONE launch (dp_lift); the sampler below is
         # the second and last launch of the batch (kernel-side repeat, hypothesis mean fused into its final store)
         x_uvxyz = getattr(model_pose, "module", model_pose).lift(input_2d, src_mask)
     return sample(model_diff, x_uvxyz, src_mask, seq, betas, eta=eta, noise=noise, n_hyp=test_times,
-                  repeat_input=True, mean_over_hyp=True)
+                  repeat_input=True, mean_over_hyp=True, targets=targets, sums=sums)
 
 
 def evaluate_shard(model_diff, x_uvxyz, targets_3d, *, src_mask=None, seq, betas, eta=0.0, test_times=1, noise=None,
@@ -47,10 +48,10 @@ def evaluate_shard(model_diff, x_uvxyz, targets_3d, *, src_mask=None, seq, betas
         if noise is not None:   # noise is [T, H*n, 17, 5] hypothesis-major over this shard
             T = noise.shape[0]
             nz = noise.reshape(T, test_times, n, 17, -1)[:, :, lo:hi].reshape(T, test_times * (hi - lo), 17, -1)
-        out = lift_and_refine(model_diff, None if x_uvxyz is None else x_uvxyz[lo:hi], model_pose=model_pose,
-                              input_2d=None if input_2d is None else input_2d[lo:hi], src_mask=src_mask, seq=seq,
-                              betas=betas, eta=eta, test_times=test_times, noise=nz)
-        pose_error_sums(out, targets_3d[lo:hi], sums=sums)
+        # sampler + metrics of the batch in one launch (two with the lifter in front)
+        lift_and_refine(model_diff, None if x_uvxyz is None else x_uvxyz[lo:hi], model_pose=model_pose,
+                        input_2d=None if input_2d is None else input_2d[lo:hi], src_mask=src_mask, seq=seq,
+                        betas=betas, eta=eta, test_times=test_times, noise=nz, targets=targets_3d[lo:hi], sums=sums)
     return sums
 
 

@@ -107,13 +107,16 @@ def _unwrap(model):
 
 
 def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_input=False, mean_over_hyp=False,
-           steps=None):
+           steps=None, targets=None, sums=None):
     """Run the DDIM loop on the device and return x_T.
 
     x: [n_hyp*n_pose,17,c] hypothesis-major (what `.repeat(test_times,1,1)` produces), or [n_pose,17,c] with
     `repeat_input=True` to let the kernel read each pose n_hyp times instead of materialising the repeat.
     noise: optional [T, n_hyp*n_pose, 17, c] standard-normal draws replacing `torch.randn_like` (:65).
     mean_over_hyp: fuse `mean(reshape(n_hyp,-1,17,c),0)` (runners/diffpose_frame.py:382) after the loop.
+    targets, sums: fused evaluation (`dp_sample_eval`): targets [n_pose,17,3] on the device and a CUDA fp64 tensor of 3
+    partial sums `[sum mpjpe, sum p_mpjpe, n]` that every finished pose is added to in the same launch (:384-387); with
+    n_hyp > 1 this needs mean_over_hyp.  Without them nothing is evaluated.
     """
     m = _unwrap(model)
     xc = m._check_x(x, m._c_in)
@@ -146,11 +149,25 @@ def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_inpu
     mb = m._mask_bytes(src_mask, dev)
     lib = _lib.load()
     mask_ptr = mb.data_ptr() if mb is not None else None
+    tg = None
+    if targets is not None:
+        if sums is None or not sums.is_cuda or sums.dtype is not torch.float64 or sums.numel() != 3:
+            raise RuntimeError("fused evaluation needs `sums`: a CUDA float64 tensor of 3 elements")
+        if n_hyp > 1 and not mean_over_hyp:
+            raise RuntimeError("fused evaluation with n_hyp > 1 evaluates the hypothesis mean: pass mean_over_hyp=True")
+        tg = targets.detach().to(device=dev, dtype=torch.float32).contiguous()
+        if tuple(tg.shape) != (n_pose, m.n_pts, 3):
+            raise RuntimeError(f"targets must be [{n_pose},{m.n_pts},3], got {tuple(tg.shape)}")
 
-    def launch(x_t, out_t, n_p, nz_t, repeated):
+    def launch(x_t, out_t, n_p, nz_t, repeated, lo=0):
         stream = torch.cuda.current_stream(dev).cuda_stream
-        rc = lib.dp_sample(m._handle, x_t.data_ptr(), 1 if repeated else 0, out_t.data_ptr(), n_p, n_hyp, steps, T,
-                           nz_t.data_ptr() if nz_t is not None else None, mask_ptr, 1 if mean_over_hyp else 0, stream)
+        if tg is None:
+            rc = lib.dp_sample(m._handle, x_t.data_ptr(), 1 if repeated else 0, out_t.data_ptr(), n_p, n_hyp, steps, T,
+                               nz_t.data_ptr() if nz_t is not None else None, mask_ptr, 1 if mean_over_hyp else 0, stream)
+        else:
+            rc = lib.dp_sample_eval(m._handle, x_t.data_ptr(), 1 if repeated else 0, out_t.data_ptr(), n_p, n_hyp, steps, T,
+                                    nz_t.data_ptr() if nz_t is not None else None, mask_ptr, 1 if mean_over_hyp else 0,
+                                    tg[lo:lo + n_p].data_ptr(), sums.data_ptr(), stream)
         if rc != 0:
             _lib.check(rc, "dp_sample")
 
@@ -175,10 +192,10 @@ def sample(model, x, src_mask, seq, b, eta=0.0, noise=None, n_hyp=1, repeat_inpu
             nzc.normal_()
             x_c = xv[lo:hi] if repeat_input else xv[:, lo:hi].reshape(k * n_hyp, m.n_pts, c).contiguous()
             if mean_over_hyp:
-                launch(x_c, ov[lo:hi], k, nzc, not repeat_input)
+                launch(x_c, ov[lo:hi], k, nzc, not repeat_input, lo)
             else:
                 o_c = torch.empty(k * n_hyp, m.n_pts, c, device=dev, dtype=torch.float32)
-                launch(x_c, o_c, k, nzc, not repeat_input)
+                launch(x_c, o_c, k, nzc, not repeat_input, lo)
                 ov[:, lo:hi] = o_c.view(n_hyp, k, m.n_pts, c)
 
     if torch.cuda.current_device() == dev.index:      # the usual case: no device switch on the per-batch path

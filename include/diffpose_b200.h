@@ -134,6 +134,16 @@ int dp_sample(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, l
               const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
               int mean_over_hyp, void* stream);
 
+/* dp_sample followed by dp_metrics on its result, in ONE launch on DP_ENGINE_TCG: the body of the evaluation loop
+ * (runners/diffpose_frame.py:365-387: generalized_steps, hypothesis mean, root-centring, mpjpe, p_mpjpe).  Every pose the
+ * kernel finishes (after the hypothesis mean when n_hyp > 1, which then requires mean_over_hyp = 1) adds its MPJPE to sums[0],
+ * its P-MPJPE to sums[1] and 1 to sums[2] from the tile it was computed in -- one warp per pose in the tile's tail, one atomic
+ * per CTA -- instead of a second kernel re-reading x_out.  targets_xyz [n_pose,n_pts,3], sums: 3 doubles on the device
+ * (accumulated into; the caller zeroes them).  Other engines run dp_sample and dp_metrics back to back. */
+int dp_sample_eval(dp_handle h, const float* x_in, int x_is_repeated, float* x_out, long n_pose, int n_hyp,
+                   const dp_step* steps_host, int n_steps, const float* noise, const unsigned char* mask,
+                   int mean_over_hyp, const float* targets_xyz, double* sums, void* stream);
+
 /* Batches that live in HOST memory.  Replaces the copy-in / sample / copy-out sequence of the evaluation loop
  * (runners/diffpose_frame.py:333-335 `input_2d.to(self.device)` ..., :365 generalized_steps, :387 `.cpu()`), which the
  * reference runs strictly one after the other, by a ring of `depth` slots: the host->device copy of batch i+1 and the

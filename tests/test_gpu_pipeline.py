@@ -160,3 +160,40 @@ def test_second_device_in_one_process():
     for eng in ("fp32", "tcx"):
         c = D.generalized_steps(x.to("cuda:1"), None, [0, 12], m1.set_engine(eng), betas())[0][-1]
         assert (c.cpu() - a.cpu()).abs().max().item() < 1e-3
+
+
+@pytest.mark.parametrize("engine", ["auto", "fp32"])
+@pytest.mark.parametrize("n,Hh", [(1, 1), (37, 1), (300, 1), (23, 5), (150, 3), (9, 10)])
+def test_fused_evaluation_equals_sampler_then_metrics(engine, n, Hh):
+    """dp_sample_eval (sampler + MPJPE / P-MPJPE partial sums in one launch on the default engine; one warp per finished pose
+    in the tile's tail) accumulates exactly what dp_sample followed by dp_metrics does -- ragged batches, several tiles per
+    CTA, hypothesis mean (poses completing across tile boundaries, H larger than a tile), accumulation over calls."""
+    dev = torch.device("cuda:0")
+    adj, diff, sd_d, _, _ = _models()
+    diff = diff.to(dev).set_engine(engine).eval()
+    seq = [0, 6]
+    x = O.synthetic_poses(n, seed=90 + n).to(dev)
+    tgt = O.synthetic_targets(x.cpu(), seed=91).to(dev)
+    g = torch.Generator().manual_seed(92)
+    noise = torch.randn(len(seq), Hh * n, 17, 5, generator=g).to(dev)
+    kw = dict(eta=1.0, noise=noise, n_hyp=Hh, repeat_input=True, mean_over_hyp=Hh > 1)
+    plain = D.sample(diff, x, None, seq, betas(), **kw)
+    want, _ = D.pose_error_sums(plain, tgt)
+    sums = torch.zeros(3, device=dev, dtype=torch.float64)
+    l0 = D._lib.launch_count()
+    fused = D.sample(diff, x, None, seq, betas(), targets=tgt, sums=sums, **kw)
+    n_launch = D._lib.launch_count() - l0
+    assert torch.equal(fused, plain)
+    np.testing.assert_allclose(sums.cpu().numpy(), want.cpu().numpy(), rtol=1e-12)
+    assert sums[2].item() == n
+    if engine == "auto":
+        assert n_launch == 1
+    D.sample(diff, x, None, seq, betas(), targets=tgt, sums=sums, **kw)          # accumulates
+    np.testing.assert_allclose(sums.cpu().numpy(), 2 * want.cpu().numpy(), rtol=1e-12)
+    # against the oracle's metrics of the oracle's sample
+    den = lambda xt, m, tt: O.gcndiff_forward(sd_d, adj, 5, 4, xt, m, tt)
+    ref = O.hypothesis_mean(O.ddim_sample(x.cpu().repeat(Hh, 1, 1), None, seq, den, betas(), eta=1.0, noise=noise.cpu())[0][-1], Hh)
+    m_ref = O.mpjpe(O.root_centre(ref[:, :, 2:]), O.root_centre(tgt.cpu())).item() * 1000
+    assert abs(want[0].item() / n * 1000 - m_ref) < 0.05
+    with pytest.raises(RuntimeError, match="mean_over_hyp"):
+        D.sample(diff, x.repeat(2, 1, 1), None, seq, betas(), n_hyp=2, targets=tgt, sums=sums)
