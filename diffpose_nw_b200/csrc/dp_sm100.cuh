@@ -102,12 +102,29 @@ __device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float* v) {
 #pragma unroll
   for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+// the same for 8 columns
+__device__ __forceinline__ void tmem_ld8_async(uint32_t taddr, float* v) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr) : "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 24 consecutive columns starting at taddr
+__device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v);
 // the loaded registers may only be consumed after the wait: pin every value behind it for the compiler
 template <int N>
 __device__ __forceinline__ void launder(float* v) {
 #pragma unroll
   for (int i = 0; i < N; ++i) asm volatile("" : "+f"(v[i]));
+}
+__device__ __forceinline__ void tmem_ld24(uint32_t taddr, float* v) {
+  tmem_ld16_async(taddr, v);
+  tmem_ld8_async(taddr + 16, v + 16);
+  tmem_ld_wait();
+  launder<24>(v);
 }
 // 48 consecutive columns starting at taddr
 __device__ __forceinline__ void tmem_ld48(uint32_t taddr, float* v) {

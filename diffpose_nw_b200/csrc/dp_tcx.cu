@@ -50,8 +50,10 @@ constexpr int PAIR_BYTES = 2 * ABLK_BYTES;          // an operand = (hi block, l
 constexpr int ONES_BYTES = 2 * A_LBO;               // 4128
 constexpr int BLOCKS_PER_LAYER = 14;                // each one a (hi, lo) pair of ring entries
 constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
-constexpr int kComputeThreads = 256;
+constexpr int kComputeThreads = 512;   // 16 compute warps: the fp32 shared-memory phases are latency bound, so the kernel wants warps
 constexpr int kThreads = kComputeThreads + 32;
+constexpr int kParts = kComputeThreads / TM;          // 4 threads per tile row: 24 of the 96 channels each
+constexpr int PC = H / kParts;                        // 24
 constexpr int TMEM_COLS = 512;
 constexpr int XS = 8;                // x_t / eps row stride (floats)
 
@@ -78,7 +80,7 @@ static_assert(TR * XLD * 4 <= PAIR_BYTES, "an fp32 buffer must fit the operand p
 static_assert(OFF_W % 128 == 0 && OFF_P0 % 128 == 0 && OFF_P1 % 128 == 0 && OFF_ONES % 16 == 0 && OFF_BAR % 16 == 0 && OFF_NBC % 16 == 0 &&
               OFF_XT % 16 == 0 && OFF_TE % 16 == 0, "alignment");
 
-__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t kIdescN96 = (1u << 4) | ((96u >> 3) << 17) | ((128u >> 4) << 24);
 
@@ -163,173 +165,153 @@ __device__ __forceinline__ void wait_gemm(Pipe& p) {
   tc_fence_after();
 }
 
-// Epilogues: warp w reads TMEM lanes 32*(w&3).. (its rows) and the column half (w>>2) of a 96-column accumulator.
-enum EpiKind { EPI_F32 = 0, EPI_XADD = 1, EPI_XADD_RELU = 2, EPI_RELU_SPLIT = 3, EPI_RELU_TEMB_F32 = 4 };
+// Thread map of the 16 compute warps: warp w owns tile rows 32*(w&3).. (the TMEM lanes a warp may touch) and the 24-channel
+// part (w>>2) of them.
+struct Tm {
+  int row, part;
+  uint32_t taddr;     // TMEM address of this thread's lane, column 0
+};
+__device__ __forceinline__ Tm thread_map(uint32_t tmem_base) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  Tm t;
+  t.row = (warp & 3) * 32 + lane;
+  t.part = warp >> 2;
+  t.taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+  return t;
+}
+
+// Epilogues of a 96-column accumulator: every thread handles the 24 columns of its part.
+enum EpiKind { EPI_F32 = 0, EPI_XADD = 1, EPI_RELU_SPLIT = 2 };
 
 template <int KIND>
-__device__ __forceinline__ void epilogue(uint8_t* smem, uint32_t tmem_acc, int dst_off, const float* __restrict__ temb_rows, int temb_stride) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = (warp & 3) * 32 + lane;
-  const int c0 = (warp >> 2) * 48;
-  const uint32_t taddr = tmem_acc + ((uint32_t)((warp & 3) * 32) << 16);
+__device__ __forceinline__ void epilogue(uint8_t* smem, const Tm& t, uint32_t acc_col, int dst_off) {
+  float v[PC];
+  tmem_ld24(t.taddr + acc_col + PC * t.part, v);     // (warp-collective: every lane takes part, valid row or not)
+  if (KIND == EPI_RELU_SPLIT) {
+    uint8_t* pair = smem + dst_off;
 #pragma unroll
-  for (int cc = 0; cc < 48; cc += 16) {
-    const int c = c0 + cc;
-    float v[16];
-    tmem_ld16(taddr + c, v);     // (warp-collective: every lane takes part, valid row or not)
-    if (KIND == EPI_XADD_RELU || KIND == EPI_RELU_SPLIT || KIND == EPI_RELU_TEMB_F32) {
+    for (int i = 0; i < PC; ++i) v[i] = fmaxf(v[i], 0.f);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.f);
+    for (int c = 0; c < 3; ++c) {
+      if (t.row < TR) store_split(pair, t.row, 3 * t.part + c, v + 8 * c);
+      else store_zero(pair, t.row, 3 * t.part + c);
     }
-    if (KIND == EPI_RELU_SPLIT) {
-      uint8_t* pair = smem + dst_off;
-      if (row < TR) { store_split(pair, row, c >> 3, v); store_split(pair, row, (c >> 3) + 1, v + 8); }
-      else { store_zero(pair, row, c >> 3); store_zero(pair, row, (c >> 3) + 1); }
-      continue;
-    }
-    if (row >= TR) continue;
-    if (KIND == EPI_RELU_TEMB_F32 && temb_rows != nullptr) {
-      const float* te = temb_rows + (row / NP) * temb_stride + c;
+    return;
+  }
+  if (t.row >= TR) return;
+  float* dst = reinterpret_cast<float*>(smem + (KIND == EPI_XADD ? OFF_X : dst_off)) + t.row * XLD + PC * t.part;
 #pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        const float4 t = *reinterpret_cast<const float4*>(te + i);
-        v[i] += t.x; v[i + 1] += t.y; v[i + 2] += t.z; v[i + 3] += t.w;
-      }
+  for (int i = 0; i < PC; i += 4) {
+    float4 o = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    if (KIND == EPI_XADD) {
+      const float4 x = *reinterpret_cast<float4*>(dst + i);
+      o.x += x.x; o.y += x.y; o.z += x.z; o.w += x.w;
     }
-    if (KIND == EPI_XADD || KIND == EPI_XADD_RELU) {
-      float* X = reinterpret_cast<float*>(smem + OFF_X) + row * XLD + c;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) {
-        float4 x = *reinterpret_cast<float4*>(X + i);
-        x.x += v[i]; x.y += v[i + 1]; x.z += v[i + 2]; x.w += v[i + 3];
-        *reinterpret_cast<float4*>(X + i) = x;
-      }
-    } else {   // fp32 rows into a scratch buffer
-      float* Z = reinterpret_cast<float*>(smem + dst_off) + row * XLD + c;
-#pragma unroll
-      for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(Z + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
-    }
+    *reinterpret_cast<float4*>(dst + i) = o;
   }
 }
 
-// LayerNorm of the residual stream (GraFormer.py:67-70: unbiased std, eps added to std): lanes (2r, 2r+1) own the two
-// 48-channel halves of row r.  TO_OPERAND: split into the operand pair at dst_off; else fp32 rows at dst_off.
+// LayerNorm of the residual stream (GraFormer.py:67-70: unbiased std, eps added to std): lanes 4r .. 4r+3 own the four
+// 24-channel parts of row r.  TO_OPERAND: split into the operand pair at dst_off; else fp32 rows at dst_off.
 template <bool TO_OPERAND>
 __device__ __forceinline__ void layer_norm_tile(uint8_t* smem, int dst_off, const float* __restrict__ ga, const float* __restrict__ gb) {
-  const int row = threadIdx.x >> 1, hh = threadIdx.x & 1;
-  const float* xr = reinterpret_cast<const float*>(smem + OFF_X) + min(row, TR - 1) * XLD + hh * 48;
-  float v[48];
+  const int row = threadIdx.x >> 2, q4 = threadIdx.x & 3;
+  const float* xr = reinterpret_cast<const float*>(smem + OFF_X) + min(row, TR - 1) * XLD + q4 * PC;
+  float v[PC];
 #pragma unroll
-  for (int q = 0; q < 12; ++q) {
+  for (int q = 0; q < PC / 4; ++q) {
     const float4 u = *reinterpret_cast<const float4*>(xr + 4 * q);
     v[4 * q] = u.x; v[4 * q + 1] = u.y; v[4 * q + 2] = u.z; v[4 * q + 3] = u.w;
   }
   float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 48; ++i) s += v[i];
+  for (int i = 0; i < PC; ++i) s += v[i];
   s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
   const float mean = s * (1.0f / (float)H);
   float q2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 48; ++i) { v[i] -= mean; q2 = fmaf(v[i], v[i], q2); }
+  for (int i = 0; i < PC; ++i) { v[i] -= mean; q2 = fmaf(v[i], v[i], q2); }
   q2 += __shfl_xor_sync(0xffffffffu, q2, 1);
+  q2 += __shfl_xor_sync(0xffffffffu, q2, 2);
   const float inv = 1.0f / (sqrtf(q2 * (1.0f / (float)(H - 1))) + 1e-6f);
   if (row >= TR) {
     if (TO_OPERAND) {
 #pragma unroll
-      for (int c = 0; c < 6; ++c) store_zero(smem + dst_off, row, hh * 6 + c);
+      for (int c = 0; c < 3; ++c) store_zero(smem + dst_off, row, q4 * 3 + c);
     }
     return;
   }
 #pragma unroll
-  for (int q = 0; q < 12; ++q) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(ga + hh * 48) + q), b = __ldg(reinterpret_cast<const float4*>(gb + hh * 48) + q);
+  for (int q = 0; q < PC / 4; ++q) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(ga + q4 * PC) + q), b = __ldg(reinterpret_cast<const float4*>(gb + q4 * PC) + q);
     v[4 * q] = fmaf(a.x * inv, v[4 * q], b.x); v[4 * q + 1] = fmaf(a.y * inv, v[4 * q + 1], b.y);
     v[4 * q + 2] = fmaf(a.z * inv, v[4 * q + 2], b.z); v[4 * q + 3] = fmaf(a.w * inv, v[4 * q + 3], b.w);
   }
   if (TO_OPERAND) {
 #pragma unroll
-    for (int c = 0; c < 6; ++c) store_split(smem + dst_off, row, hh * 6 + c, v + 8 * c);
+    for (int c = 0; c < 3; ++c) store_split(smem + dst_off, row, q4 * 3 + c, v + 8 * c);
   } else {
-    float* y = reinterpret_cast<float*>(smem + dst_off) + row * XLD + hh * 48;
+    float* y = reinterpret_cast<float*>(smem + dst_off) + row * XLD + q4 * PC;
 #pragma unroll
-    for (int q = 0; q < 12; ++q) *reinterpret_cast<float4*>(y + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    for (int q = 0; q < PC / 4; ++q) *reinterpret_cast<float4*>(y + 4 * q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
   }
 }
 
 // Multi-head attention over the joints of each pose (GraFormer.py:99-113) in fp32.  q: this thread's row straight from
-// the accumulator columns [0, 96) in TMEM; k, v: fp32 rows in S0 / S1.  One thread per (row, head pair): warp w owns rows
-// 32*(w&3).. and heads 2*(w>>2), 2*(w>>2)+1.  The outputs stay in registers until every thread has finished reading v
-// (S1 aliases the operand pair the result is written to).
-__device__ __forceinline__ void attention_tile(uint8_t* smem, uint32_t tmem_base, int out_pair_off) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int row = (warp & 3) * 32 + lane;
-  const int h0 = (warp >> 2) * 2;
-  const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+// the accumulator columns [0, 96) in TMEM; k, v: fp32 rows in S0 / S1.  One thread per (row, head): warp w owns rows
+// 32*(w&3).. and head w>>2.  The output stays in registers until every thread has finished reading v (S1 aliases the
+// operand pair the result is written to).
+__device__ __forceinline__ void attention_tile(uint8_t* smem, const Tm& t, int out_pair_off) {
+  const int h = t.part;
   const float* maskf = reinterpret_cast<const float*>(smem + OFF_MASK);
   const float* K = reinterpret_cast<const float*>(smem + OFF_P0);
   const float* V = reinterpret_cast<const float*>(smem + OFF_P1);
   const float scale = 1.0f / sqrtf(24.0f);
-  const int p = min(row, TR - 1) / NP;
-  float o[48];
+  const int p = min(t.row, TR - 1) / NP;
+  float q[PC];
+  tmem_ld24(t.taddr + PC * h, q);
+  float sc[NP];
+  float mx = -INFINITY;
 #pragma unroll
-  for (int hl = 0; hl < 2; ++hl) {
-    const int h = h0 + hl;
-    float q[24];
-    {
-      float a[16], b[16];
-      tmem_ld16_async(taddr + 24 * h, a);
-      tmem_ld16_async(taddr + 24 * h + 8, b);
-      tmem_ld_wait();
-      launder<16>(a);
-      launder<16>(b);
+  for (int j = 0; j < NP; ++j) {
+    const float* kr = K + (p * NP + j) * XLD + PC * h;
+    float s = 0.f;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) q[i] = a[i];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) q[16 + i] = b[8 + i];
+    for (int c = 0; c < 6; ++c) {
+      const float4 kv = *reinterpret_cast<const float4*>(kr + 4 * c);
+      s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s); s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
     }
-    float sc[NP];
-    float mx = -INFINITY;
+    s = s * scale;
+    if (maskf[j] == 0.f) s = -1e9f;
+    sc[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  float sum = 0.f;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const float* kr = K + (p * NP + j) * XLD + 24 * h;
-      float s = 0.f;
+  for (int j = 0; j < NP; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
+  const float inv = 1.0f / sum;
+  float o[PC];
 #pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const float4 kv = *reinterpret_cast<const float4*>(kr + 4 * c);
-        s = fmaf(q[4 * c], kv.x, s); s = fmaf(q[4 * c + 1], kv.y, s); s = fmaf(q[4 * c + 2], kv.z, s); s = fmaf(q[4 * c + 3], kv.w, s);
-      }
-      s = s * scale;
-      if (maskf[j] == 0.f) s = -1e9f;
-      sc[j] = s;
-      mx = fmaxf(mx, s);
-    }
-    float sum = 0.f;
+  for (int e = 0; e < PC; ++e) o[e] = 0.f;
 #pragma unroll
-    for (int j = 0; j < NP; ++j) { sc[j] = expf(sc[j] - mx); sum += sc[j]; }
-    const float inv = 1.0f / sum;
-    float* oh = o + 24 * hl;
+  for (int j = 0; j < NP; ++j) {
+    const float* vr = V + (p * NP + j) * XLD + PC * h;
+    const float pj = sc[j] * inv;
 #pragma unroll
-    for (int e = 0; e < 24; ++e) oh[e] = 0.f;
-#pragma unroll
-    for (int j = 0; j < NP; ++j) {
-      const float* vr = V + (p * NP + j) * XLD + 24 * h;
-      const float pj = sc[j] * inv;
-#pragma unroll
-      for (int c = 0; c < 6; ++c) {
-        const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c);
-        oh[4 * c] = fmaf(pj, vv.x, oh[4 * c]); oh[4 * c + 1] = fmaf(pj, vv.y, oh[4 * c + 1]);
-        oh[4 * c + 2] = fmaf(pj, vv.z, oh[4 * c + 2]); oh[4 * c + 3] = fmaf(pj, vv.w, oh[4 * c + 3]);
-      }
+    for (int c = 0; c < 6; ++c) {
+      const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c);
+      o[4 * c] = fmaf(pj, vv.x, o[4 * c]); o[4 * c + 1] = fmaf(pj, vv.y, o[4 * c + 1]);
+      o[4 * c + 2] = fmaf(pj, vv.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(pj, vv.w, o[4 * c + 3]);
     }
   }
   tc_fence_before();
   bar_compute();               // everybody is done with k and v
   uint8_t* pair = smem + out_pair_off;
 #pragma unroll
-  for (int c = 0; c < 6; ++c) {
-    if (row < TR) store_split(pair, row, 3 * h0 + c, o + 8 * c);
-    else store_zero(pair, row, 3 * h0 + c);
+  for (int c = 0; c < 3; ++c) {
+    if (t.row < TR) store_split(pair, t.row, 3 * h + c, o + 8 * c);
+    else store_zero(pair, t.row, 3 * h + c);
   }
 }
 
@@ -338,7 +320,7 @@ __device__ __forceinline__ void lhat_to_operand(uint8_t* smem, int src_off, int 
   const int row = threadIdx.x & 127;
   uint8_t* pair = smem + pair_off;
   if (row >= TR) {
-    for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) store_zero(pair, row, kc);
+    for (int kc = threadIdx.x >> 7; kc < 12; kc += kParts) store_zero(pair, row, kc);
     return;
   }
   const float* Y = reinterpret_cast<const float*>(smem + src_off);
@@ -347,7 +329,7 @@ __device__ __forceinline__ void lhat_to_operand(uint8_t* smem, int src_off, int 
   float co[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) co[j] = lh[i * NP + j];
-  for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+  for (int kc = threadIdx.x >> 7; kc < 12; kc += kParts) {
     float acc[8];
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -373,7 +355,7 @@ __device__ __forceinline__ void lhat_residual(uint8_t* smem, int src_off, const 
   float co[NP];
 #pragma unroll
   for (int j = 0; j < NP; ++j) co[j] = lh[i * NP + j];
-  for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
+  for (int kc = threadIdx.x >> 7; kc < 12; kc += kParts) {
     float acc[8];
     const float4 bb0 = __ldg(reinterpret_cast<const float4*>(b2 + kc * 8)), bb1 = __ldg(reinterpret_cast<const float4*>(b2 + kc * 8 + 4));
     acc[0] = bb0.x; acc[1] = bb0.y; acc[2] = bb0.z; acc[3] = bb0.w; acc[4] = bb1.x; acc[5] = bb1.y; acc[6] = bb1.z; acc[7] = bb1.w;
@@ -391,57 +373,49 @@ __device__ __forceinline__ void lhat_residual(uint8_t* smem, int src_off, const 
   }
 }
 
-// One part of the Chebyshev input panel [V | T1 V | T2 V] (ChebConv.py:74-112) as a split operand pair; V = fp32 rows at
-// src_off.  ORDER 0: V itself, 1: T1 V, 2: T2 V (fp32 over the neighbour list).  ORDER 12: T1 V -> pair_off and T2 V ->
-// pair_off2 in one pass over the neighbours.
-template <int ORDER>
-__device__ __forceinline__ void cheb_part(uint8_t* smem, int src_off, int pair_off, int pair_off2 = 0) {
+// fp32 rows at src_off -> split operand pair (the A side of a Chebyshev block: [v W0 | v W1 | v W2] from one operand)
+__device__ __forceinline__ void rows_to_operand(uint8_t* smem, int src_off, int pair_off) {
   const int row = threadIdx.x & 127;
   uint8_t* pair = smem + pair_off;
-  uint8_t* pair2 = smem + pair_off2;
-  if (row >= TR) {
-    for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
-      store_zero(pair, row, kc);
-      if (ORDER == 12) store_zero(pair2, row, kc);
-    }
-    return;
-  }
   const float* V = reinterpret_cast<const float*>(smem + src_off);
-  if (ORDER == 0) {
-    for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
-      const float* src = V + row * XLD + kc * 8;
-      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
-      const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-      store_split(pair, row, kc, u);
-    }
-    return;
+  for (int kc = threadIdx.x >> 7; kc < 12; kc += kParts) {
+    if (row >= TR) { store_zero(pair, row, kc); continue; }
+    const float* src = V + row * XLD + kc * 8;
+    const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
+    const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
+    store_split(pair, row, kc, u);
   }
+}
+
+// Chebyshev block, aggregation AFTER the products (ChebConv.py:74-88: sum_k T_k (v W_k) = (v W0) + T1 (v W1) + T2 (v W2)):
+// the three products sit in the accumulators at columns 0 (with the bias), 96 and 192.  Phase 1: Y1, Y2 -> fp32 rows S0, S1.
+// Phase 2 (after a barrier): out = relu(acc0 + T1 Y1 + T2 Y2) over the neighbour list of the row's joint, 24 channels per
+// thread.  One GEMM wait per block instead of three, and T1 / T2 share one pass.
+__device__ __forceinline__ void cheb_stage_y(uint8_t* smem, const Tm& t) {
+  epilogue<EPI_F32>(smem, t, 96, OFF_P0);
+  epilogue<EPI_F32>(smem, t, 192, OFF_P1);
+}
+__device__ __forceinline__ void cheb_aggregate(uint8_t* smem, const Tm& t, float* out) {
+  tmem_ld24(t.taddr + PC * t.part, out);
+  if (t.row >= TR) return;
   const int* nbi = reinterpret_cast<const int*>(smem + OFF_NBI);
   const float2* nbc = reinterpret_cast<const float2*>(smem + OFF_NBC);
-  const int p = row / NP, i = row - p * NP;
-  int nj[NNB];
-  float2 nc[NNB];
+  const float* Y1 = reinterpret_cast<const float*>(smem + OFF_P0) + PC * t.part;
+  const float* Y2 = reinterpret_cast<const float*>(smem + OFF_P1) + PC * t.part;
+  const int p = t.row / NP, i = t.row - p * NP;
 #pragma unroll
-  for (int n = 0; n < NNB; ++n) { nj[n] = p * NP + nbi[i * NNB + n]; nc[n] = nbc[i * NNB + n]; }
-  for (int kc = threadIdx.x >> 7; kc < 12; kc += 2) {
-    float a1[8], a2[8];
+  for (int n = 0; n < NNB; ++n) {
+    const int rj = (p * NP + nbi[i * NNB + n]) * XLD;
+    const float2 cf = nbc[i * NNB + n];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { a1[e] = 0.f; a2[e] = 0.f; }
-#pragma unroll
-    for (int n = 0; n < NNB; ++n) {
-      const float* src = V + nj[n] * XLD + kc * 8;
-      const float4 u0 = *reinterpret_cast<const float4*>(src), u1 = *reinterpret_cast<const float4*>(src + 4);
-      const float u[8] = {u0.x, u0.y, u0.z, u0.w, u1.x, u1.y, u1.z, u1.w};
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        if (ORDER == 1 || ORDER == 12) a1[e] = fmaf(nc[n].x, u[e], a1[e]);
-        if (ORDER == 2 || ORDER == 12) a2[e] = fmaf(nc[n].y, u[e], a2[e]);
-      }
+    for (int c = 0; c < PC; c += 4) {
+      const float4 a = *reinterpret_cast<const float4*>(Y1 + rj + c), b = *reinterpret_cast<const float4*>(Y2 + rj + c);
+      out[c] = fmaf(cf.y, b.x, fmaf(cf.x, a.x, out[c])); out[c + 1] = fmaf(cf.y, b.y, fmaf(cf.x, a.y, out[c + 1]));
+      out[c + 2] = fmaf(cf.y, b.z, fmaf(cf.x, a.z, out[c + 2])); out[c + 3] = fmaf(cf.y, b.w, fmaf(cf.x, a.w, out[c + 3]));
     }
-    if (ORDER == 1) store_split(pair, row, kc, a1);
-    else if (ORDER == 2) store_split(pair, row, kc, a2);
-    else { store_split(pair, row, kc, a1); store_split(pair2, row, kc, a2); }
   }
+#pragma unroll
+  for (int c = 0; c < PC; ++c) out[c] = fmaxf(out[c], 0.f);
 }
 
 __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg inl) {
@@ -498,7 +472,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
   const int L = a.n_layer;
   const int ci = a.c_in, co = a.c_out;
 
-  if (warp == 8) {
+  if (warp == kComputeThreads / 32) {
     // ---------------------------------------------------------------- weight producer (TMA bulk copies): the (hi, lo) blocks
     // of a layer in the order the kernel consumes them
     if (lane == 0) {
@@ -515,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
     __syncwarp();
   } else {
     // ---------------------------------------------------------------- compute warps
+    const Tm t = thread_map(tmem_base);
     for (long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const long g0 = tile * TP;
       const int npose = (int)min((long)TP, a.n_rows - g0);
@@ -552,26 +527,26 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
         }
         bar_compute();
         {
-          const int row = tid & 127, hh = tid >> 7;
+          const int row = tid & 127, part = tid >> 7;
           if (row < TR) {
-            float acc[48];
+            float acc[PC];
 #pragma unroll
-            for (int g = 0; g < 12; ++g) {
-              const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.bin + hh * 48) + g);
+            for (int g = 0; g < PC / 4; ++g) {
+              const float4 b4 = __ldg(reinterpret_cast<const float4*>(w.bin + part * PC) + g);
               acc[4 * g] = b4.x; acc[4 * g + 1] = b4.y; acc[4 * g + 2] = b4.z; acc[4 * g + 3] = b4.w;
             }
             for (int k = 0; k < 3 * ci; ++k) {
               const float bv = Bin[row * 16 + k];
 #pragma unroll
-              for (int g = 0; g < 12; ++g) {
-                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w.win + k * H + hh * 48) + g);
+              for (int g = 0; g < PC / 4; ++g) {
+                const float4 w4 = __ldg(reinterpret_cast<const float4*>(w.win + k * H + part * PC) + g);
                 acc[4 * g] = fmaf(bv, w4.x, acc[4 * g]); acc[4 * g + 1] = fmaf(bv, w4.y, acc[4 * g + 1]);
                 acc[4 * g + 2] = fmaf(bv, w4.z, acc[4 * g + 2]); acc[4 * g + 3] = fmaf(bv, w4.w, acc[4 * g + 3]);
               }
             }
 #pragma unroll
-            for (int g = 0; g < 12; ++g)
-              *reinterpret_cast<float4*>(X + row * XLD + hh * 48 + 4 * g) = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
+            for (int g = 0; g < PC / 4; ++g)
+              *reinterpret_cast<float4*>(X + row * XLD + part * PC + 4 * g) = make_float4(acc[4 * g], acc[4 * g + 1], acc[4 * g + 2], acc[4 * g + 3]);
           }
         }
         bar_compute();
@@ -600,11 +575,11 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          epilogue<EPI_F32>(smem, tmem_base + 96, OFF_P0, nullptr, 0);     // k -> S0
-          epilogue<EPI_F32>(smem, tmem_base + 192, OFF_P1, nullptr, 0);    // v -> S1 (the GEMMs have finished reading pair 1)
+          epilogue<EPI_F32>(smem, t, 96, OFF_P0);      // k -> S0
+          epilogue<EPI_F32>(smem, t, 192, OFF_P1);     // v -> S1 (the GEMMs have finished reading pair 1)
           tc_fence_before();
           bar_compute();
-          attention_tile(smem, tmem_base, OFF_P0);                          // (syncs inside) -> pair 0
+          attention_tile(smem, t, OFF_P0);              // (syncs inside) -> pair 0
           publish_operand();
           if (tid == 0) {
             tc_fence_after();
@@ -612,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          epilogue<EPI_XADD>(smem, tmem_base, 0, nullptr, 0);
+          epilogue<EPI_XADD>(smem, t, 0, 0);
           tc_fence_before();
           bar_compute();
           // ======== x = x + GraphNet(LN1(x))
@@ -627,8 +602,8 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          epilogue<EPI_RELU_SPLIT>(smem, tmem_base, OFF_P0, nullptr, 0);   // relu(h[:, 0:96]) -> pair 0
-          epilogue<EPI_RELU_SPLIT>(smem, tmem_base + 96, OFF_P1, nullptr, 0);   // relu(h[:, 96:192]) -> pair 1
+          epilogue<EPI_RELU_SPLIT>(smem, t, 0, OFF_P0);    // relu(h[:, 0:96]) -> pair 0
+          epilogue<EPI_RELU_SPLIT>(smem, t, 96, OFF_P1);   // relu(h[:, 96:192]) -> pair 1
           publish_operand();
           if (tid == 0) {
             tc_fence_after();
@@ -637,85 +612,102 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          epilogue<EPI_F32>(smem, tmem_base + 192, OFF_P1, nullptr, 0);    // z -> S1
+          epilogue<EPI_F32>(smem, t, 192, OFF_P1);     // z -> S1
           tc_fence_before();
           bar_compute();
           lhat_residual(smem, OFF_P1, Lw.b2);
           bar_compute();
-          // ======== x = x + GC2(GC1(x) + temb)
-          cheb_part<0>(smem, OFF_X, OFF_P0);
+          // ======== x = x + GC2(GC1(x) + temb): each block = one operand, three products, aggregation in the epilogue
+          rows_to_operand(smem, OFF_X, OFF_P0);
           publish_operand();
           if (tid == 0) {
             tc_fence_after();
-            issue_gemm(pp, sbase, tmem_base, OFF_P0, false, true);
+            issue_gemm(pp, sbase, tmem_base, OFF_P0, false, true);          // x W0 + b
+            issue_gemm(pp, sbase, tmem_base + 96, OFF_P0, false, false);    // x W1
+            issue_gemm(pp, sbase, tmem_base + 192, OFF_P0, false, false);   // x W2
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          cheb_part<12>(smem, OFF_X, OFF_P0, OFF_P1);
-          publish_operand();
-          if (tid == 0) {
-            tc_fence_after();
-            issue_gemm(pp, sbase, tmem_base, OFF_P0, true, false);
-            issue_gemm(pp, sbase, tmem_base, OFF_P1, true, false);
-            umma_commit(pp.done);
-          }
-          wait_gemm(pp);
-          epilogue<EPI_RELU_TEMB_F32>(smem, tmem_base, OFF_P1, a.has_temb ? te : nullptr, a.forward_only ? H : 0);   // h1 -> S1
+          cheb_stage_y(smem, t);
           tc_fence_before();
           bar_compute();
-          cheb_part<0>(smem, OFF_P1, OFF_P0);
+          {
+            float h1[PC];
+            cheb_aggregate(smem, t, h1);        // relu(GC1(x))
+            if (a.has_temb && t.row < TR) {     // + temb (gcndiff.py:51): per pose for a forward call, per step for the sampler
+              const float* tr = te + (a.forward_only ? (t.row / NP) * H : 0) + PC * t.part;
+#pragma unroll
+              for (int c = 0; c < PC; c += 4) {
+                const float4 tv = *reinterpret_cast<const float4*>(tr + c);
+                h1[c] += tv.x; h1[c + 1] += tv.y; h1[c + 2] += tv.z; h1[c + 3] += tv.w;
+              }
+            }
+            tc_fence_before();
+            bar_compute();                       // everybody is done with Y1, Y2 (they alias the operand pairs)
+            uint8_t* pair = smem + OFF_P0;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+              if (t.row < TR) store_split(pair, t.row, 3 * t.part + c, h1 + 8 * c);
+              else store_zero(pair, t.row, 3 * t.part + c);
+            }
+          }
           publish_operand();
           if (tid == 0) {
             tc_fence_after();
             issue_gemm(pp, sbase, tmem_base, OFF_P0, false, true);
+            issue_gemm(pp, sbase, tmem_base + 96, OFF_P0, false, false);
+            issue_gemm(pp, sbase, tmem_base + 192, OFF_P0, false, false);
             umma_commit(pp.done);
           }
           wait_gemm(pp);
-          cheb_part<1>(smem, OFF_P1, OFF_P0);
-          publish_operand();
-          if (tid == 0) {
-            tc_fence_after();
-            issue_gemm(pp, sbase, tmem_base, OFF_P0, true, false);
-            umma_commit(pp.done);
+          cheb_stage_y(smem, t);
+          tc_fence_before();
+          bar_compute();
+          {
+            float h2[PC];
+            cheb_aggregate(smem, t, h2);        // relu(GC2(h1))
+            if (t.row < TR) {
+              float* xr = X + t.row * XLD + PC * t.part;
+#pragma unroll
+              for (int c = 0; c < PC; c += 4) {
+                float4 x = *reinterpret_cast<float4*>(xr + c);
+                x.x += h2[c]; x.y += h2[c + 1]; x.z += h2[c + 2]; x.w += h2[c + 3];
+                *reinterpret_cast<float4*>(xr + c) = x;
+              }
+            }
           }
-          wait_gemm(pp);
-          cheb_part<2>(smem, OFF_P1, OFF_P0);
-          publish_operand();
-          if (tid == 0) {
-            tc_fence_after();
-            issue_gemm(pp, sbase, tmem_base, OFF_P0, true, false);
-            umma_commit(pp.done);
-          }
-          wait_gemm(pp);
-          epilogue<EPI_XADD_RELU>(smem, tmem_base, 0, nullptr, 0);
           tc_fence_before();
           bar_compute();
         }
 
-        // ---- output ChebConv (N = c_out <= 5): U_k = X Wout_k on the CUDA cores, then eps = b + U0 + T1 U1 + T2 U2
+        // ---- output ChebConv (N = c_out <= 5): U_k = X Wout_k on the CUDA cores, then eps = b + U0 + T1 U1 + T2 U2.
+        //      Wout [3*96][c_out] is staged in shared memory first (a warp reads one channel row at a time: broadcasts).
+        float* wsm = reinterpret_cast<float*>(smem + OFF_P1);
+        for (int i = tid; i < 3 * H * co; i += kComputeThreads) wsm[i] = __ldg(w.wout + i);
+        bar_compute();
         {
-          float* U = reinterpret_cast<float*>(smem + OFF_P0);   // [2][128][16]
-          const int row = tid & 127, hh = tid >> 7;
+          float* U = reinterpret_cast<float*>(smem + OFF_P0);   // [4][128][16]
+          const int row = tid & 127, part = tid >> 7;
           float acc[15];
 #pragma unroll
           for (int i = 0; i < 15; ++i) acc[i] = 0.f;
           if (row < TR) {
-            for (int cq = 0; cq < 12; ++cq) {
-              const float4 xv = *reinterpret_cast<const float4*>(X + row * XLD + hh * 48 + cq * 4);
+            for (int cq = 0; cq < PC / 4; ++cq) {
+              const float4 xv = *reinterpret_cast<const float4*>(X + row * XLD + part * PC + cq * 4);
               const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
               for (int e = 0; e < 4; ++e) {
-                const int c = hh * 48 + cq * 4 + e;
+                const int c = part * PC + cq * 4 + e;
 #pragma unroll
                 for (int k3 = 0; k3 < 3; ++k3)
 #pragma unroll
                   for (int n = 0; n < 5; ++n)
-                    if (n < co) acc[k3 * 5 + n] = fmaf(xs[e], __ldg(w.wout + (k3 * H + c) * co + n), acc[k3 * 5 + n]);
+                    if (n < co) acc[k3 * 5 + n] = fmaf(xs[e], wsm[(k3 * H + c) * co + n], acc[k3 * 5 + n]);
               }
             }
           }
 #pragma unroll
-          for (int i = 0; i < 15; ++i) U[(hh * TM + row) * 16 + i] = acc[i];
+          for (int i = 0; i < 15; ++i) U[(part * TM + row) * 16 + i] = acc[i];
         }
         bar_compute();
         {
@@ -723,13 +715,18 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
           for (int idx = tid; idx < TR * co; idx += kComputeThreads) {
             const int r = idx / co, n = idx - r * co;
             const int p = r / NP, i = r - p * NP;
-            float v = __ldg(w.bout + n) + U[r * 16 + n] + U[(TM + r) * 16 + n];
+            float v = __ldg(w.bout + n);
+#pragma unroll
+            for (int pt = 0; pt < kParts; ++pt) v += U[(pt * TM + r) * 16 + n];
 #pragma unroll
             for (int q = 0; q < NNB; ++q) {
               const int rj = p * NP + nbi[i * NNB + q];
               const float2 cf = nbc[i * NNB + q];
-              v = fmaf(cf.x, U[rj * 16 + 5 + n] + U[(TM + rj) * 16 + 5 + n], v);
-              v = fmaf(cf.y, U[rj * 16 + 10 + n] + U[(TM + rj) * 16 + 10 + n], v);
+              float u1 = 0.f, u2 = 0.f;
+#pragma unroll
+              for (int pt = 0; pt < kParts; ++pt) { u1 += U[(pt * TM + rj) * 16 + 5 + n]; u2 += U[(pt * TM + rj) * 16 + 10 + n]; }
+              v = fmaf(cf.x, u1, v);
+              v = fmaf(cf.y, u2, v);
             }
             ep[r * XS + n] = v;
           }

@@ -349,3 +349,29 @@ def test_metrics_kernel_many_poses_vs_oracle():
     np.testing.assert_allclose(pp[:, 1].cpu().numpy(), want_p, atol=1e-6)
     s = sums.cpu().numpy()
     assert s[2] == n and abs(s[0] - want_m.astype(np.float64).sum()) < 1e-4 and abs(s[1] - want_p.sum()) < 1e-4
+
+
+@pytest.mark.parametrize("engine", ["fp32", "tcx", "auto"])
+def test_long_schedule_device_step_table(engine):
+    """Schedules of more than 64 steps travel through a device-side step table that is uploaded when the schedule CHANGES
+    (not per call): 100 steps (a 100-entry beta schedule, every timestep) against the oracle, the same schedule again
+    (cached table), then a different eta (re-upload) -- on every engine."""
+    adj = D.adj_mx_from_edges()
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(adj, O.default_config())
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    model = model.to(dev()).set_engine(engine).eval()
+    b100 = torch.from_numpy(D.get_beta_schedule("linear", beta_start=1e-4, beta_end=2e-3, num_diffusion_timesteps=100)).float()
+    seq = list(range(100))
+    n = 5
+    x = O.synthetic_poses(n, seed=13)
+    g = torch.Generator().manual_seed(14)
+    noise = torch.randn(len(seq), n, 17, 5, generator=g)
+    den = lambda xt, m, tt: O.gcndiff_forward(sd, adj, 5, 4, xt, m, tt)
+    tol = {"fp32": FP32_TOL, "tcx": 1e-4, "tcg": TC_TOL_X}[model.engine()]
+    for eta in (0.5, 0.5, 1.0):
+        ref = O.ddim_sample(x, None, seq, den, b100, eta=eta, noise=noise)[0][-1]
+        out = D.generalized_steps(x.to(dev()), None, seq, model, b100, eta=eta, noise=noise.to(dev()))[0][-1].cpu()
+        err = (out - ref).abs().max().item()
+        print(f"T=100 eta={eta} / {model.engine()}: max|dx|={err:.2e}")
+        assert err < tol
