@@ -18,7 +18,7 @@
 //
 // It serves dp_forward for both model kinds (GCNdiff with per-sample timesteps, GCNpose uv -> xyz, optionally fused with
 // the runner's root-centring + concat into uvxyz, runners/diffpose_frame.py:337-343) and is selectable for the sampler.
-// Result: <= 2e-5 from the fp32 oracle (tests/test_gpu_tc.py) at ~8x the speed of the fp32 FMA engine.
+// Result: <= 2e-5 from the fp32 oracle (tests/test_gpu_tc.py) at ~6x the speed of the fp32 FMA engine.
 //
 // Reference semantics: see the list at the top of dp_simt.cu (same functions, same file:line).
 #include <cuda_fp16.h>
