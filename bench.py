@@ -278,9 +278,6 @@ def main():
     batch_bytes = B * ROW_BYTES
     if B * pool_n > 4_000_000:       # bound the host-side generation for the million-pose workloads
         pool_n = 2
-    if os.environ.get("BENCH_POOL_N"):      # experiment switch: a small, L2-resident pool (NOT a valid bench configuration)
-        pool_n = int(os.environ["BENCH_POOL_N"])
-        config["l2"] = f"EXPERIMENT: pool of {pool_n} buffers (may be L2 resident)"
     base = O.synthetic_poses(min(B, 131072), seed=1 + rank)
     if base.shape[0] < B:
         base = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1)[:B].contiguous()
@@ -364,10 +361,13 @@ def main():
     gc.enable()
     launches = _lib.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
+    ms_ranks = [ms / args.steps]
     if dist is not None:
         tms = torch.tensor([ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-        ms = float(tms.item())
+        allms = [torch.zeros_like(tms) for _ in range(world)]
+        dist.all_gather(allms, tms)
+        ms_ranks = [float(t.item()) / args.steps for t in allms]
+        ms = max(float(t.item()) for t in allms)          # the job is as fast as its slowest rank
     poses_per_step = B_total if strong else world * B        # whole job
     value = poses_per_step * args.steps / (ms * 1e-3)
 
@@ -450,7 +450,7 @@ def main():
             "dtype": "f16 operands / f32 accumulate (tcgen05)" if model.engine() == "tcg" else ("f16 hi+lo operands / f32 accumulate (tcgen05)" if model.engine() == "tcx" else "f32"),
             "data": "synthetic",
             "config": config,
-            "detail": {"timing": timing_note, "engine": model.engine(), "lifter_engine": pose_model.forward_engine() if two_stage else None, "batch_this_rank": B,
+            "detail": {"timing": timing_note, "ms_per_step_by_rank": [round(v, 5) for v in ms_ranks], "engine": model.engine(), "lifter_engine": pose_model.forward_engine() if two_stage else None, "batch_this_rank": B,
                        "launch": {"grid": ll[0], "block": ll[1], "smem": ll[2], "poses_per_tile": ll[3], "tiles": ll[5]}},
             "e2e": e2e,
             "gpu_launches": int(launches),

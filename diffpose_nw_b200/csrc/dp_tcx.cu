@@ -49,7 +49,8 @@ constexpr int ABLK_BYTES = 12 * A_LBO;              // 24768
 constexpr int PAIR_BYTES = 2 * ABLK_BYTES;          // an operand = (hi block, lo block)
 constexpr int ONES_BYTES = 2 * A_LBO;               // 4128
 constexpr int BLOCKS_PER_LAYER = 14;                // each one a (hi, lo) pair of ring entries
-constexpr int NNB = 9;               // max |2-hop neighbourhood| in the H36M tree (support of T2 = 2L^2 - I)
+constexpr int NNB = NP;              // neighbour-list capacity: any graph.  The lists are padded to the longest row of the graph in
+                                     // use (9 = the largest 2-hop neighbourhood of the H36M tree, support of T2 = 2L^2 - I)
 constexpr int kComputeThreads = 512;   // 16 compute warps: the fp32 shared-memory phases are latency bound, so the kernel wants warps
 constexpr int kThreads = kComputeThreads + 32;
 constexpr int kParts = kComputeThreads / TM;          // 4 threads per tile row: 24 of the 96 channels each
@@ -67,8 +68,8 @@ constexpr int OFF_ONES = OFF_P1 + al128(PAIR_BYTES);       // constant-one K sla
 constexpr int OFF_W = al128(OFF_ONES + ONES_BYTES);        // weight ring
 constexpr int OFF_XT = OFF_W + NSTAGE * WBLK_BYTES;        // x_t [128][8] fp32
 constexpr int OFF_EP = OFF_XT + TM * XS * 4;               // eps [128][8] fp32
-constexpr int OFF_NBI = OFF_EP + TM * XS * 4;              // neighbour index  [17][9] int
-constexpr int OFF_NBC = al16(OFF_NBI + NP * NNB * 4);      // neighbour coeffs [17][9] float2 (T1, T2)
+constexpr int OFF_NBI = OFF_EP + TM * XS * 4;              // neighbour index  [17][17] int, then the per-row counts [17]
+constexpr int OFF_NBC = al16(OFF_NBI + (NP * NNB + NP) * 4);   // neighbour coeffs [17][17] float2 (T1, T2)
 constexpr int OFF_LH = al16(OFF_NBC + NP * NNB * 8);       // L^ [17][17]
 constexpr int OFF_TE = al16(OFF_LH + NP * NP * 4);         // temb rows of the current layer: [7][96] (forward) or [96] (sampler)
 constexpr int OFF_MASK = OFF_TE + TP * H * 4;              // key mask [32]
@@ -395,7 +396,7 @@ __device__ __forceinline__ void cheb_stage_y(uint8_t* smem, const Tm& t) {
   epilogue<EPI_F32>(smem, t, 96, OFF_P0);
   epilogue<EPI_F32>(smem, t, 192, OFF_P1);
 }
-__device__ __forceinline__ void cheb_aggregate(uint8_t* smem, const Tm& t, float* out) {
+__device__ __forceinline__ void cheb_aggregate(uint8_t* smem, const Tm& t, int nnb, float* out) {
   tmem_ld24(t.taddr + PC * t.part, out);
   if (t.row >= TR) return;
   const int* nbi = reinterpret_cast<const int*>(smem + OFF_NBI);
@@ -403,8 +404,8 @@ __device__ __forceinline__ void cheb_aggregate(uint8_t* smem, const Tm& t, float
   const float* Y1 = reinterpret_cast<const float*>(smem + OFF_P0) + PC * t.part;
   const float* Y2 = reinterpret_cast<const float*>(smem + OFF_P1) + PC * t.part;
   const int p = t.row / NP, i = t.row - p * NP;
-#pragma unroll
-  for (int n = 0; n < NNB; ++n) {
+#pragma unroll 3
+  for (int n = 0; n < nnb; ++n) {
     const int rj = (p * NP + nbi[i * NNB + n]) * XLD;
     const float2 cf = nbc[i * NNB + n];
 #pragma unroll
@@ -454,12 +455,13 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
   }
   if (tid < 32) maskf[tid] = (tid < NP && a.mask && a.mask[tid] == 0) ? 0.f : 1.f;
   if (tid < NP) {
-    // neighbour list of joint tid: columns where T1 or T2 is non-zero, padded with (self, 0, 0)
+    // neighbour list of joint tid: columns where T1 or T2 is non-zero, padded with (self, 0, 0) up to the capacity
     int n = 0;
     for (int j = 0; j < NP; ++j) {
       const float c1 = __ldg(w.t1 + tid * NP + j), c2 = __ldg(w.t2 + tid * NP + j);
-      if ((c1 != 0.f || c2 != 0.f) && n < NNB) { nbi[tid * NNB + n] = j; nbc[tid * NNB + n] = make_float2(c1, c2); ++n; }
+      if (c1 != 0.f || c2 != 0.f) { nbi[tid * NNB + n] = j; nbc[tid * NNB + n] = make_float2(c1, c2); ++n; }
     }
+    nbi[NP * NNB + tid] = n;
     for (; n < NNB; ++n) { nbi[tid * NNB + n] = tid; nbc[tid * NNB + n] = make_float2(0.f, 0.f); }
   }
   fence_async_smem();
@@ -467,6 +469,8 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  int nnb = 1;                         // longest neighbour list of this graph (every loop over a list runs to it)
+  for (int j = 0; j < NP; ++j) nnb = max(nnb, nbi[NP * NNB + j]);
 
   const long n_tiles = (a.n_rows + TP - 1) / TP;
   const int L = a.n_layer;
@@ -515,8 +519,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
           if (r < TR) {
             const int p = r / NP, i = r - p * NP;
             v0 = xt[r * XS + c];
-#pragma unroll
-            for (int n = 0; n < NNB; ++n) {
+            for (int n = 0; n < nnb; ++n) {
               const float u = xt[(p * NP + nbi[i * NNB + n]) * XS + c];
               const float2 cf = nbc[i * NNB + n];
               v1 = fmaf(cf.x, u, v1);
@@ -633,7 +636,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
           bar_compute();
           {
             float h1[PC];
-            cheb_aggregate(smem, t, h1);        // relu(GC1(x))
+            cheb_aggregate(smem, t, nnb, h1);   // relu(GC1(x))
             if (a.has_temb && t.row < TR) {     // + temb (gcndiff.py:51): per pose for a forward call, per step for the sampler
               const float* tr = te + (a.forward_only ? (t.row / NP) * H : 0) + PC * t.part;
 #pragma unroll
@@ -665,7 +668,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
           bar_compute();
           {
             float h2[PC];
-            cheb_aggregate(smem, t, h2);        // relu(GC2(h1))
+            cheb_aggregate(smem, t, nnb, h2);   // relu(GC2(h1))
             if (t.row < TR) {
               float* xr = X + t.row * XLD + PC * t.part;
 #pragma unroll
@@ -718,8 +721,7 @@ __global__ void __launch_bounds__(kThreads, 1) tcx_kernel(TcxArgs a, StepsArg in
             float v = __ldg(w.bout + n);
 #pragma unroll
             for (int pt = 0; pt < kParts; ++pt) v += U[(pt * TM + r) * 16 + n];
-#pragma unroll
-            for (int q = 0; q < NNB; ++q) {
+            for (int q = 0; q < nnb; ++q) {
               const int rj = p * NP + nbi[i * NNB + q];
               const float2 cf = nbc[i * NNB + q];
               float u1 = 0.f, u2 = 0.f;

@@ -197,3 +197,34 @@ def test_fused_evaluation_equals_sampler_then_metrics(engine, n, Hh):
     assert abs(want[0].item() / n * 1000 - m_ref) < 0.05
     with pytest.raises(RuntimeError, match="mean_over_hyp"):
         D.sample(diff, x.repeat(2, 1, 1), None, seq, betas(), n_hyp=2, targets=tgt, sums=sums)
+
+
+def test_sampler_call_is_cuda_graph_capturable():
+    """include/diffpose_b200.h: a dp_sample call that neither grows a buffer nor changes a long schedule only enqueues work,
+    so it can be captured into a CUDA graph (programmatic-dependent-launch attribute included) and replayed."""
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    model = D.FusedGCNdiff(D.adj_mx_from_edges(), O.default_config()).to(dev).eval()
+    seq = [0, 12]
+    x = O.synthetic_poses(300, seed=5).to(dev)
+    tgt = O.synthetic_targets(x.cpu()).to(dev)
+    want = D.sample(model, x, None, seq, betas(), n_hyp=3, repeat_input=True, mean_over_hyp=True)     # also warms every cache
+    sums = torch.zeros(3, device=dev, dtype=torch.float64)
+    static_x = x.clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        D.sample(model, static_x, None, seq, betas(), n_hyp=3, repeat_input=True, mean_over_hyp=True, targets=tgt, sums=sums)
+    torch.cuda.current_stream().wait_stream(s)
+    sums.zero_()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        out = D.sample(model, static_x, None, seq, betas(), n_hyp=3, repeat_input=True, mean_over_hyp=True, targets=tgt, sums=sums)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want) and sums[2].item() == 3 * 300
+    static_x.copy_(x.flip(0))
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(out, want.flip(0))

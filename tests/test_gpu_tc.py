@@ -248,6 +248,37 @@ def test_tcg_denser_graph():
     assert (out32 - ref).abs().max().item() < 2e-5
 
 
+def test_tcx_denser_graph():
+    """The split-precision engine walks per-joint neighbour lists for T1 / T2: they must cover ANY adjacency, not only the
+    <= 9 two-hop neighbours of the H36M tree.  A hub joined to every joint (T2 rows with 17 entries): forward (GCNdiff and
+    the GCNpose lifter) and sampler against the oracle."""
+    edges = list(D.H36M_EDGES) + [(0, j) for j in range(1, 17)]
+    adj = D.adj_mx_from_edges(17, edges)
+    assert ((O.cheb_basis(adj)[2] != 0).sum(1) > 9).any()
+    torch.manual_seed(3)
+    model = D.FusedGCNdiff(adj, O.default_config())
+    sd = O.perturb_state_dict({k: v.detach().clone() for k, v in model.state_dict().items()}, seed=14)
+    model.load_state_dict(sd)
+    model = model.to(dev())
+    x = O.synthetic_poses(30, seed=18)
+    tt = torch.linspace(0, 40, 30)
+    eps = model(x.to(dev()), None, tt.to(dev()), 0).cpu()
+    assert model.last_launch()[4] == ENGINE_ID["tcx"]
+    ref = O.gcndiff_forward(sd, adj, 5, 4, x, None, tt)
+    assert (eps - ref).abs().max().item() < 2e-5 * max(1.0, ref.abs().max().item())
+    seq = [0, 12]
+    ref_s = O.ddim_sample(x, None, seq, lambda a, m, t_: O.gcndiff_forward(sd, adj, 5, 4, a, m, t_), betas())[0][-1]
+    out = D.generalized_steps(x.to(dev()), None, seq, model.set_engine("tcx"), betas())[0][-1].cpu()
+    assert (out - ref_s).abs().max().item() < TCX_TOL
+    torch.manual_seed(4)
+    pose = D.FusedGCNpose(adj, O.default_config(coords_dim=[2, 3]))
+    sdp = {k: v.detach().clone() for k, v in pose.state_dict().items()}
+    uv = x[:, :, :2].contiguous()
+    xyz = pose.to(dev())(uv.to(dev()), None).cpu()
+    refp = O.gcnpose_forward(sdp, adj, 5, 4, uv, None)
+    assert (xyz - refp).abs().max().item() < 2e-5 * max(1.0, refp.abs().max().item())
+
+
 def test_tcg_long_schedule_steps_on_device():
     """More than 64 DDIM steps: the step scalars no longer travel by value but through a device array."""
     cfg = O.default_config()

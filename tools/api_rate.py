@@ -1,5 +1,7 @@
-"""Host-side cost of the drop-in call exactly as runners/diffpose_frame.py:365 makes it (betas and mask on the GPU,
-optionally a DataParallel wrapper): time per call on the host vs wall time per call (GPU only).
+"""Rate of the drop-in call exactly as runners/diffpose_frame.py:365 makes it (betas and mask on the GPU, optionally a
+DataParallel wrapper): time per call seen by the host loop vs wall time per call (GPU only).  NOTE: in a GPU-bound loop the
+"host" figure is launch-queue back-pressure (it approaches the kernel time); the actual host cost of a call is what
+tools/host_path_profile.py measures into an idle queue (17.6 us).
 
     python tools/api_rate.py
 """
