@@ -1,4 +1,4 @@
-// sm_100a building blocks shared by the tensor-core engines (dp_tc.cu, dp_tc2.cu): mbarrier, TMA bulk copy, proxy and
+// sm_100a building blocks shared by the tensor-core engines (dp_tc2.cu, dp_tcx.cu) and the UMMA lab (dp_lab.cu): mbarrier, TMA bulk copy, proxy and
 // tcgen05 fences, TMEM allocation / load / store, tcgen05.mma issue (shared-memory and TMEM A operand), UMMA descriptors
 // for the canonical SWIZZLE_NONE layouts, fp16 packing.  Everything is inline PTX; nothing here depends on an engine's
 // shared-memory map.
@@ -173,7 +173,7 @@ __device__ __forceinline__ float ex2(float x) {
   return y;
 }
 
-// 64-bit descriptor form of the same (first engine, UMMA lab)
+// 64-bit descriptor form of the same (split-precision engine, UMMA lab)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
   return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
 }

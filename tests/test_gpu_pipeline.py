@@ -141,6 +141,18 @@ def test_host_stream_matches_direct_calls():
         assert g.shape == w.shape and torch.equal(g, w)
     with pytest.raises(RuntimeError, match="exceeds"):
         hs.submit(O.synthetic_poses(65).pin_memory())
+    # hypotheses: kernel-side repeat + fused mean, through the same ring (eta = 0: HostStream draws no noise)
+    want3 = [D.sample(model, b.to(dev), None, seq, betas(), n_hyp=3, repeat_input=True, mean_over_hyp=True).cpu() for b in batches[:4]]
+    hs3 = D.HostStream(model, batch=64, seq=seq, betas=betas(), test_times=3, depth=2)
+    got3 = []
+    for b in batches[:4]:
+        r = hs3.submit(b)
+        if r is not None:
+            got3.append(r.clone())
+    got3 += [t.clone() for t in hs3.drain()]
+    assert len(got3) == 4 and all(torch.equal(g, w) for g, w in zip(got3, want3))
+    with pytest.raises(RuntimeError, match="eta = 0"):
+        D.HostStream(model, batch=64, seq=seq, betas=betas(), eta=1.0)
 
 
 def test_second_device_in_one_process():
