@@ -340,9 +340,10 @@ def main():
     barrier()
     # The barrier + synchronize leave the GPU idle (for milliseconds under NCCL), and its SM clock needs ~15 of these 0.1 ms
     # steps to come back (tools/first_steps.py: 148, 111, 111, 108, ... 102 us per step after an idle gap).  A lead-in of
-    # untimed steps between the synchronisation and the first event hands the timed K steps a busy, full-clock GPU; the
+    # untimed steps (3 ms) between the synchronisation and the first event hands the timed K steps a busy, full-clock GPU; the
     # timed region itself is exactly K steps between two CUDA events, followed by barrier + synchronize.
-    lead_in = min(10, ramp)
+    lead_in = min(30, ramp)     # 10 were enough for one process; behind an 8-rank NCCL barrier the idle gap is longer (every rank measured
+                                # 0.1004-0.1027 ms per step in the 20-step window against 0.0973 in a 2000-step run with 10)
     for i in range(lead_in):
         out = step(args.steps + args.warmup + i)
     timing_note = (f"{ramp} set-up + {args.warmup} warm-up steps, barrier + synchronize, {lead_in} untimed lead-in steps, CUDA event, "
