@@ -382,7 +382,9 @@ __device__ __forceinline__ __half* tall_elem(uint8_t* smem, int which, int trow,
 
 // ------------------------------------------------------------------------------------------------ the kernel
 // TRACE = true compiles the clock64() stamps of dp_set_trace in; the production instantiation carries none of it.
-template <bool TRACE>
+// EVAL = true compiles the fused evaluation tail (dp_sample_eval) in: ~3 000 instructions that the plain sampler instantiation
+// does not carry either.
+template <bool TRACE, bool EVAL>
 __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg inl) {
   auto signal_ready = [](Ctx& c) { signal_ready_t<TRACE>(c); };
   auto signal_ready_tmem = [](Ctx& c) { signal_ready_t<TRACE, false>(c); };
@@ -776,7 +778,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           xt[(p * PS + rem / ci) * XS + rem % ci] = a.x_in[src * (NP * ci) + rem];
         }
       }
-      if (a.gt != nullptr) {        // targets of the poses this tile finishes: requested now, read in the tile's tail
+      if ((EVAL && a.gt != nullptr)) {        // targets of the poses this tile finishes: requested now, read in the tile's tail
         float* evg = reinterpret_cast<float*>(smem + OFF_EV) + EV_FLOATS;
         for (int idx = tid; idx < npose * NP * 3; idx += kComputeThreads) {
           const int p = idx / (NP * 3);
@@ -1014,7 +1016,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
             if (h == a.n_hyp - 1) {
               const float mval = __fdiv_rn(macc, (float)a.n_hyp);
               a.out[(size_t)b * NP * co + tid] = mval;
-              if (a.gt != nullptr && tid % co >= co - 3) reinterpret_cast<float*>(smem + OFF_EV)[p * (NP * 3) + (tid / co) * 3 + tid % co - (co - 3)] = mval;
+              if ((EVAL && a.gt != nullptr) && tid % co >= co - 3) reinterpret_cast<float*>(smem + OFF_EV)[p * (NP * 3) + (tid / co) * 3 + tid % co - (co - 3)] = mval;
             }
           }
         }
@@ -1023,10 +1025,10 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
           const int p = idx / (NP * co), rem = idx - p * (NP * co);
           const float xv = xt[(p * PS + rem / co) * XS + rem % co];
           a.out[(size_t)g0 * NP * co + idx] = xv;
-          if (a.gt != nullptr && rem % co >= co - 3) reinterpret_cast<float*>(smem + OFF_EV)[p * (NP * 3) + (rem / co) * 3 + rem % co - (co - 3)] = xv;
+          if ((EVAL && a.gt != nullptr) && rem % co >= co - 3) reinterpret_cast<float*>(smem + OFF_EV)[p * (NP * 3) + (rem / co) * 3 + rem % co - (co - 3)] = xv;
         }
       }
-      if (a.gt != nullptr) {
+      if ((EVAL && a.gt != nullptr)) {
         // Fused evaluation tail (runners/diffpose_frame.py:382-387): one warp per finished pose of this tile -- at most 7, on 8
         // compute warps -- computes MPJPE and P-MPJPE from the xyz just stored and the targets requested at the tile's start.
         bar_compute();
@@ -1049,7 +1051,7 @@ __global__ void __launch_bounds__(kThreads, 1) tc2_kernel(Tc2Args a, StepsArg in
       }
       bar_compute();
     }
-    if (a.gt != nullptr) {     // one atomic per CTA and quantity
+    if ((EVAL && a.gt != nullptr)) {     // one atomic per CTA and quantity
       double* red = reinterpret_cast<double*>(smem + OFF_STAT);      // [3][8], free after the last tile
       if (lane == 0) { red[warp] = ev1; red[8 + warp] = ev2; red[16 + warp] = evn; }
       bar_compute();
@@ -1249,8 +1251,9 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
   static bool configured[64] = {};          // function attributes are per device
   bool& done = configured[m->device & 63];
   if (!done) {
-    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    DP_CUDA(cudaFuncSetAttribute(tc2_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     done = true;
   }
   const size_t wbytes = (size_t)m->d.n_layer * BLOCKS_PER_LAYER * WBLK_BYTES;
@@ -1268,8 +1271,9 @@ static int tc2_launch(dp_model* m, Tc2Args& a, const StepsArg* inl, cudaStream_t
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (a.trace != nullptr) DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<true>, a, *inl));
-  else DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<false>, a, *inl));
+  if (a.gt != nullptr) DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<false, true>, a, *inl));
+  else if (a.trace != nullptr) DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<true, false>, a, *inl));
+  else DP_CUDA(cudaLaunchKernelEx(&cfg, tc2_kernel<false, false>, a, *inl));
   count_launch();
   m->last_launch[0] = grid; m->last_launch[1] = kThreads; m->last_launch[2] = SMEM_BYTES;
   m->last_launch[3] = TP; m->last_launch[4] = DP_ENGINE_TCG; m->last_launch[5] = n_tiles;
