@@ -350,7 +350,10 @@ __global__ void __launch_bounds__(kThreads, 1) simt_kernel(SimtArgs a, StepsArg 
 
 // Time-embedding table: out[i][l][:] = temb_proj_l(swish(dense1(swish(dense0(sincos(t_i))))))
 // (gcndiff.py:15-33, :103-106, :51).  One CTA evaluates kTB timesteps so weight reads are shared.
-constexpr int kTB = 4;
+// kTB = 4 for a sampler schedule (a handful of timesteps: latency matters), 12 for per-sample timesteps of a forward call
+// (thousands: every CTA streams the 0.7 MB of embedding weights from L2, so more timesteps per CTA = fewer passes).  The
+// arithmetic per timestep is the same in both (one accumulator chain per timestep): results are bit-identical.
+template <int kTB>
 __global__ void temb_kernel(const Weights* wp, Dims d, const float* __restrict__ t_dev, int t_stride, StepsArg inl,
                             long n_t, float* __restrict__ out) {
   extern __shared__ float sm[];
@@ -473,9 +476,20 @@ int simt_temb(dp_model* m, const float* t_dev, int t_stride, const StepsArg* inl
   if (rc != DP_OK) return rc;
   StepsArg dummy{};
   const int H = d.hid;
+  if (n_t >= 64) {
+    constexpr int kTB = 12;
+    const size_t smem = (size_t)kTB * (H + 8 * H) * sizeof(float);      // 41.5 KB at hid = 96 (48 KB without opt-in: hid <= 111)
+    if (smem <= 48 * 1024) {
+      temb_kernel<kTB><<<(unsigned)((n_t + kTB - 1) / kTB), 4 * H, smem, s>>>(m->dw, d, t_dev, t_stride, inl ? *inl : dummy, n_t, m->temb);
+      count_launch();
+      DP_CUDA(cudaGetLastError());
+      return DP_OK;
+    }
+  }
+  constexpr int kTB = 4;
   const size_t smem = (size_t)kTB * (H + 8 * H) * sizeof(float);
   const long grid = (n_t + kTB - 1) / kTB;
-  temb_kernel<<<(unsigned)grid, 4 * H, smem, s>>>(m->dw, d, t_dev, t_stride, inl ? *inl : dummy, n_t, m->temb);
+  temb_kernel<kTB><<<(unsigned)grid, 4 * H, smem, s>>>(m->dw, d, t_dev, t_stride, inl ? *inl : dummy, n_t, m->temb);
   count_launch();
   DP_CUDA(cudaGetLastError());
   return DP_OK;
