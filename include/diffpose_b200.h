@@ -17,7 +17,9 @@
  *     dp_metrics only enqueue work on it.  Exceptions, all off the per-batch path: dp_pack synchronises the stream once
  *     (it stages host-side graph matrices); dp_sample synchronises once when a schedule of MORE than 64 steps changes
  *     (the new step table is uploaded from the handle's own copy); scratch buffers (time-embedding table, hypothesis
- *     scratch of the non-default engines) grow with cudaMalloc the first time a larger batch or schedule is seen.
+ *     scratch of the non-default engines) grow with cudaMalloc the first time a larger batch or schedule is seen, and the
+ *     first dp_forward / dp_lift after a dp_pack builds the split-precision weight blocks of DP_ENGINE_TCX (pack kernels
+ *     on `stream`; one cudaMalloc the very first time).
  *     A call that neither grows a buffer nor changes a long schedule is CUDA-graph capturable.
  *   - a handle belongs to the device that was current at dp_create; calls made with another device current return
  *     DP_ERR_STATE.  One host thread per handle; one process per GPU.
