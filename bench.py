@@ -398,14 +398,14 @@ def main():
                          targets=targets if wl.get("with_metrics") else None, sums=msums if wl.get("with_metrics") else None)
             host_out[i & 1].copy_(o, non_blocking=True)
 
-        if wl.get("with_metrics"):
-            hs = None
+        host_tg = targets.cpu().pin_memory() if (wl.get("with_metrics") and hs is not None) else None      # evaluation: targets travel with the batch
+        hs_sums = msums if host_tg is not None else None
         # at least 200 batches (>= 20 ms): a host-clock window of 20 batches (2 ms) measures scheduling jitter of the rank
         # processes rather than the pipeline (8 ranks, max over ranks: 0.87 "efficiency" at 20 batches, 0.99 at 2000)
         e_steps = min(max(args.steps, 200), 2000) if poses_per_step * H * T <= 200000 else max(3, min(args.steps, 200))
         last = None
         for i in range(3):
-            e2e_serial(i) if hs is None else hs.submit(host_in[i & 1])
+            e2e_serial(i) if hs is None else hs.submit(host_in[i & 1], host_tg, hs_sums)
         if hs is not None:
             hs.drain()
         barrier()
@@ -414,7 +414,7 @@ def main():
             if hs is None:
                 e2e_serial(i)
             else:
-                r = hs.submit(host_in[i & 1])
+                r = hs.submit(host_in[i & 1], host_tg, hs_sums)
                 last = r if r is not None else last
         if hs is not None:
             tail = hs.drain()
@@ -426,7 +426,8 @@ def main():
             dist.all_reduce(tms, op=dist.ReduceOp.MAX)
             e_ms = float(tms.item())
         assert torch.isfinite(last if last is not None else host_out[0]).all()
-        e2e = {"value": poses_per_step * e_steps / (e_ms * 1e-3), "unit": "poses/s", "h2d_bytes_per_step": B * 17 * 2 * 4 if two_stage else B * ROW_BYTES,
+        e2e = {"value": poses_per_step * e_steps / (e_ms * 1e-3), "unit": "poses/s",
+               "h2d_bytes_per_step": B * 17 * 2 * 4 if two_stage else B * ROW_BYTES + (B * 17 * 3 * 4 if host_tg is not None else 0),
                "d2h_bytes_per_step": out_rows * ROW_BYTES, "steps": e_steps, "ms_per_step": e_ms / e_steps,
                "how": "pinned host buffers; " + ("HostStream (H2D / kernel / D2H of neighbouring batches overlap)" if hs is not None else "copy -> call -> copy per step")}
     elif dist is not None:

@@ -39,6 +39,7 @@ SIGNATURES = {
     "dp_sample_eval": (_I, [_P, _P, _I, _P, _L, _I, ctypes.POINTER(DpStep), _I, _P, _P, _I, _P, _P, _P]),
     "dp_hstream_create": (_I, [ctypes.POINTER(_P), _P, _L, _I, _I, _I]),
     "dp_hstream_submit": (_I, [_P, _P, _L, ctypes.POINTER(DpStep), _I, _P, _P, _P, _P, ctypes.POINTER(_I)]),
+    "dp_hstream_submit_eval": (_I, [_P, _P, _P, _P, _L, ctypes.POINTER(DpStep), _I, _P, _P, _P, _P, ctypes.POINTER(_I)]),
     "dp_hstream_wait": (_I, [_P, _I]),
     "dp_hstream_destroy": (None, [_P]),
     "dp_metrics": (_I, [_P, _I, _I, _P, _L, _I, _P, _P, _P]),

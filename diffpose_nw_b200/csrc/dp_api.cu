@@ -502,7 +502,7 @@ struct dp_hstream {
   int n_hyp = 1, mean = 0, depth = 0, head = 0;
   size_t in_floats = 0, out_floats = 0;
   cudaStream_t s_in = nullptr, s_out = nullptr;
-  std::vector<float*> x_dev, out_dev;
+  std::vector<float*> x_dev, out_dev, gt_dev;     // per slot: input, result, and (evaluation) the targets of the batch
   std::vector<cudaEvent_t> ev_in, ev_done, ev_out;
 };
 
@@ -525,7 +525,13 @@ int dp_hstream_create(dp_hstream_t* out, dp_handle h, long max_pose, int n_hyp, 
     cudaEvent_t e0 = nullptr, e1 = nullptr, e2 = nullptr;
     e = cudaMalloc(reinterpret_cast<void**>(&a), s->in_floats * sizeof(float));
     if (e == cudaSuccess) { s->x_dev.push_back(a); e = cudaMalloc(reinterpret_cast<void**>(&b), s->out_floats * sizeof(float)); }
-    if (e == cudaSuccess) { s->out_dev.push_back(b); e = cudaEventCreateWithFlags(&e0, cudaEventDisableTiming); }
+    if (e == cudaSuccess) {
+      s->out_dev.push_back(b);
+      float* g = nullptr;
+      e = cudaMalloc(reinterpret_cast<void**>(&g), (size_t)max_pose * h->d.n_pts * 3 * sizeof(float));
+      if (e == cudaSuccess) s->gt_dev.push_back(g);
+    }
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&e0, cudaEventDisableTiming);
     if (e == cudaSuccess) { s->ev_in.push_back(e0); e = cudaEventCreateWithFlags(&e1, cudaEventDisableTiming); }
     if (e == cudaSuccess) { s->ev_done.push_back(e1); e = cudaEventCreateWithFlags(&e2, cudaEventDisableTiming); }
     if (e == cudaSuccess) s->ev_out.push_back(e2);
@@ -539,8 +545,8 @@ int dp_hstream_create(dp_hstream_t* out, dp_handle h, long max_pose, int n_hyp, 
   return DP_OK;
 }
 
-int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp_step* steps_host, int n_steps, const float* noise_dev,
-                      const unsigned char* mask_dev, float* out_host, void* stream, int* slot_out) {
+static int hstream_submit(dp_hstream_t s, const float* x_host, const float* targets_host, double* sums_dev, long n_pose, const dp_step* steps_host,
+                          int n_steps, const float* noise_dev, const unsigned char* mask_dev, float* out_host, void* stream, int* slot_out) {
   DP_REQUIRE(s && x_host && out_host && steps_host && slot_out, "dp_hstream_submit: NULL argument");
   DP_REQUIRE(n_pose >= 1 && n_pose <= s->max_pose, "dp_hstream_submit: batch exceeds the max_pose this stream was created for");
   DP_TRY(check_device(s->h, "dp_hstream_submit"));
@@ -551,11 +557,16 @@ int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp
   // H2D on the copy-in stream, once the kernel that last read this slot's input has finished
   DP_CUDA(cudaStreamWaitEvent(s->s_in, s->ev_done[k], 0));
   DP_CUDA(cudaMemcpyAsync(s->x_dev[k], x_host, in_bytes, cudaMemcpyHostToDevice, s->s_in));
+  if (targets_host != nullptr)
+    DP_CUDA(cudaMemcpyAsync(s->gt_dev[k], targets_host, (size_t)n_pose * s->h->d.n_pts * 3 * sizeof(float), cudaMemcpyHostToDevice, s->s_in));
   DP_CUDA(cudaEventRecord(s->ev_in[k], s->s_in));
   // the sampler on the caller's stream, once the input is there and the slot's previous result has left the device
   DP_CUDA(cudaStreamWaitEvent(cs, s->ev_in[k], 0));
   DP_CUDA(cudaStreamWaitEvent(cs, s->ev_out[k], 0));
-  DP_TRY(dp_sample(s->h, s->x_dev[k], 0, s->out_dev[k], n_pose, s->n_hyp, steps_host, n_steps, noise_dev, mask_dev, s->mean, stream));
+  if (targets_host != nullptr)
+    DP_TRY(dp_sample_eval(s->h, s->x_dev[k], 0, s->out_dev[k], n_pose, s->n_hyp, steps_host, n_steps, noise_dev, mask_dev, s->mean, s->gt_dev[k], sums_dev, stream));
+  else
+    DP_TRY(dp_sample(s->h, s->x_dev[k], 0, s->out_dev[k], n_pose, s->n_hyp, steps_host, n_steps, noise_dev, mask_dev, s->mean, stream));
   DP_CUDA(cudaEventRecord(s->ev_done[k], cs));
   // D2H on the copy-out stream
   DP_CUDA(cudaStreamWaitEvent(s->s_out, s->ev_done[k], 0));
@@ -564,6 +575,17 @@ int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp
   *slot_out = k;
   s->head = (k + 1) % s->depth;
   return DP_OK;
+}
+
+int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp_step* steps_host, int n_steps, const float* noise_dev,
+                      const unsigned char* mask_dev, float* out_host, void* stream, int* slot_out) {
+  return hstream_submit(s, x_host, nullptr, nullptr, n_pose, steps_host, n_steps, noise_dev, mask_dev, out_host, stream, slot_out);
+}
+
+int dp_hstream_submit_eval(dp_hstream_t s, const float* x_host, const float* targets_host, double* sums_dev, long n_pose, const dp_step* steps_host,
+                           int n_steps, const float* noise_dev, const unsigned char* mask_dev, float* out_host, void* stream, int* slot_out) {
+  DP_REQUIRE(targets_host && sums_dev, "dp_hstream_submit_eval: NULL argument");
+  return hstream_submit(s, x_host, targets_host, sums_dev, n_pose, steps_host, n_steps, noise_dev, mask_dev, out_host, stream, slot_out);
 }
 
 int dp_hstream_wait(dp_hstream_t s, int slot) {
@@ -578,6 +600,7 @@ void dp_hstream_destroy(dp_hstream_t s) {
   if (s->s_out) cudaStreamSynchronize(s->s_out);
   for (float* p : s->x_dev) cudaFree(p);
   for (float* p : s->out_dev) cudaFree(p);
+  for (float* p : s->gt_dev) cudaFree(p);
   for (cudaEvent_t e : s->ev_in) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_done) cudaEventDestroy(e);
   for (cudaEvent_t e : s->ev_out) cudaEventDestroy(e);

@@ -115,16 +115,17 @@ class HostStream:
         self._pending = collections.deque()        # (slot, host buffer, rows, input tensor kept alive until its copy has run)
 
     def _collect(self):
-        slot, hb, n, _ = self._pending.popleft()
+        slot, hb, n = self._pending.popleft()[:3]
         rc = self._lib.dp_hstream_wait(self.hs, slot)
         if rc != 0:
             from . import _lib
             _lib.check(rc, "dp_hstream_wait")
         return self.out_host[hb][:n]
 
-    def submit(self, x_host):
+    def submit(self, x_host, targets_host=None, sums=None):
         """Queue one pinned host batch [n<=B,17,c] (fp32, contiguous).  Returns the oldest finished result when the ring is
-        full, else None."""
+        full, else None.  With `targets_host` [n,17,3] (pinned fp32) and `sums` (CUDA fp64 [3]) the batch's MPJPE / P-MPJPE
+        partial sums are accumulated by the sampler launch itself (`dp_hstream_submit_eval`)."""
         n = x_host.shape[0]
         if n > self.B:
             raise RuntimeError(f"batch of {n} poses exceeds the {self.B} this HostStream was built for")
@@ -137,12 +138,21 @@ class HostStream:
         hb = self._hpos
         self._hpos = (hb + 1) % len(self.out_host)
         stream = torch.cuda.current_stream(self.dev).cuda_stream
-        rc = self._lib.dp_hstream_submit(self.hs, x_host.data_ptr(), n, self.steps, self.T, None, self._mask_ptr,
-                                         self.out_host[hb].data_ptr(), stream, self._slot_ref)
+        if targets_host is None:
+            rc = self._lib.dp_hstream_submit(self.hs, x_host.data_ptr(), n, self.steps, self.T, None, self._mask_ptr,
+                                             self.out_host[hb].data_ptr(), stream, self._slot_ref)
+        else:
+            if (targets_host.is_cuda or targets_host.dtype is not torch.float32 or not targets_host.is_contiguous()
+                    or tuple(targets_host.shape) != (n, 17, 3)):
+                raise RuntimeError(f"targets_host must be a contiguous fp32 HOST tensor [{n},17,3]")
+            if sums is None or not sums.is_cuda or sums.dtype is not torch.float64 or sums.numel() != 3:
+                raise RuntimeError("fused evaluation needs `sums`: a CUDA float64 tensor of 3 elements")
+            rc = self._lib.dp_hstream_submit_eval(self.hs, x_host.data_ptr(), targets_host.data_ptr(), sums.data_ptr(), n, self.steps, self.T,
+                                                  None, self._mask_ptr, self.out_host[hb].data_ptr(), stream, self._slot_ref)
         if rc != 0:
             from . import _lib
             _lib.check(rc, "dp_hstream_submit")
-        self._pending.append((self._slot.value, hb, n, x_host))
+        self._pending.append((self._slot.value, hb, n, x_host, targets_host))
         return ret
 
     def drain(self):

@@ -163,6 +163,12 @@ typedef struct dp_hstream* dp_hstream_t;
 int dp_hstream_create(dp_hstream_t* out, dp_handle h, long max_pose, int n_hyp, int mean_over_hyp, int depth);
 int dp_hstream_submit(dp_hstream_t s, const float* x_host, long n_pose, const dp_step* steps_host, int n_steps, const float* noise_dev,
                       const unsigned char* mask_dev, float* out_host, void* stream, int* slot);
+/* The same with the evaluation fused in (dp_sample_eval): targets_host [n_pose,n_pts,3] (pinned) travels with the batch, the
+ * kernel adds the batch's MPJPE / P-MPJPE sums to sums_dev (3 doubles on the device) -- the whole body of the evaluation
+ * loop (runners/diffpose_frame.py:333-387) per batch: two H2D copies, one launch, one D2H copy. */
+int dp_hstream_submit_eval(dp_hstream_t s, const float* x_host, const float* targets_host, double* sums_dev, long n_pose,
+                           const dp_step* steps_host, int n_steps, const float* noise_dev, const unsigned char* mask_dev, float* out_host,
+                           void* stream, int* slot);
 int dp_hstream_wait(dp_hstream_t s, int slot);
 void dp_hstream_destroy(dp_hstream_t s);
 

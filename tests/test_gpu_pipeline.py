@@ -153,6 +153,22 @@ def test_host_stream_matches_direct_calls():
     assert len(got3) == 4 and all(torch.equal(g, w) for g, w in zip(got3, want3))
     with pytest.raises(RuntimeError, match="eta = 0"):
         D.HostStream(model, batch=64, seq=seq, betas=betas(), eta=1.0)
+    # evaluation fused into the ring: targets travel with each batch, the sums accumulate on the device
+    tgts = [O.synthetic_targets(b, seed=70 + i).pin_memory() for i, b in enumerate(batches)]
+    want_sums = torch.zeros(3, device=dev, dtype=torch.float64)
+    for w, tg in zip(want, tgts):
+        D.pose_error_sums(w.to(dev), tg.to(dev), sums=want_sums)
+    sums = torch.zeros(3, device=dev, dtype=torch.float64)
+    hs4 = D.HostStream(model, batch=64, seq=seq, betas=betas(), depth=3)
+    got4 = []
+    for b, tg in zip(batches, tgts):
+        r = hs4.submit(b, tg, sums)
+        if r is not None:
+            got4.append(r.clone())
+    got4 += [t.clone() for t in hs4.drain()]
+    torch.cuda.synchronize()
+    assert all(torch.equal(g, w) for g, w in zip(got4, want))
+    np.testing.assert_allclose(sums.cpu().numpy(), want_sums.cpu().numpy(), rtol=1e-12)
 
 
 def test_second_device_in_one_process():
